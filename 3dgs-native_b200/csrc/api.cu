@@ -1,0 +1,234 @@
+// api.cu -- context management and the two whole-operator entry points:
+//   gsb_forward  = render_gaussians (reference forward.py:629-894)
+//   gsb_backward = backward         (reference backward.py:955-1196)
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* v0, int64_t* k1, int32_t* v1,
+                            int32_t* final_vals, int64_t n, int begin_bit, int end_bit, bool* result_in_second);
+extern int g_blend_fwd_ppt;
+extern int g_blend_bwd_ppt;
+
+int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+int gsb_check_cuda(gsb_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GSB_OK;
+  return gsb_set_error(ctx, GSB_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+// grow-only device buffer; contents are NOT preserved
+int gsb_grow(gsb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_elems, size_t elem_size, cudaStream_t s) {
+  if (need_elems <= *cap) return GSB_OK;
+  int64_t new_cap = need_elems + need_elems / 4 + 1024;
+  if (*ptr) {
+    GSB_CUDA(ctx, cudaStreamSynchronize(s));
+    GSB_CUDA(ctx, cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+  }
+  cudaError_t e = cudaMalloc(ptr, (size_t)new_cap * elem_size);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    cudaGetLastError();
+    return gsb_set_error(ctx, GSB_ERR_NOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)(new_cap * (int64_t)elem_size),
+                         cudaGetErrorString(e));
+  }
+  *cap = new_cap;
+  return GSB_OK;
+}
+
+int gsb_reserve_binning(gsb_ctx* ctx, cudaStream_t s, int64_t num_rendered) {
+  if (num_rendered <= ctx->bin_cap) return GSB_OK;
+  int64_t c0 = ctx->bin_cap, c1 = ctx->bin_cap, c2 = ctx->bin_cap, c3 = ctx->bin_cap;
+  int rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->keys_a, &c0, num_rendered, sizeof(int64_t), s)) != GSB_OK) return rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->keys_b, &c1, num_rendered, sizeof(int64_t), s)) != GSB_OK) return rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->vals_a, &c2, num_rendered, sizeof(int32_t), s)) != GSB_OK) return rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->vals_b, &c3, num_rendered, sizeof(int32_t), s)) != GSB_OK) return rc;
+  ctx->bin_cap = c0 < c1 ? c0 : c1;
+  ctx->bin_cap = ctx->bin_cap < c2 ? ctx->bin_cap : c2;
+  ctx->bin_cap = ctx->bin_cap < c3 ? ctx->bin_cap : c3;
+  return GSB_OK;
+}
+
+static int reserve_per_gaussian(gsb_ctx* ctx, cudaStream_t s, int64_t n) {
+  if (n <= ctx->n_cap) return GSB_OK;
+  int64_t c0 = ctx->n_cap, c1 = ctx->n_cap;
+  int rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->tiles_touched, &c0, n, sizeof(int32_t), s)) != GSB_OK) return rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->dcov3d, &c1, n * 6, sizeof(float), s)) != GSB_OK) return rc;
+  ctx->n_cap = c0 < c1 / 6 ? c0 : c1 / 6;
+  return GSB_OK;
+}
+
+GSB_API int gsb_version(void) { return GSB_VERSION; }
+
+GSB_API int gsb_create(gsb_ctx** out, int device) {
+  if (!out) return GSB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return GSB_ERR_CUDA;  // no CUDA device: there is no CPU fallback
+  }
+  if (device < 0 || device >= count) return GSB_ERR_INVALID;
+  gsb_ctx* ctx = new gsb_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete ctx;
+    return GSB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  if (cudaMalloc((void**)&ctx->d_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->sort_small, (256 + 16) * sizeof(uint32_t)) != cudaSuccess) {
+    delete ctx;
+    return GSB_ERR_NOMEM;
+  }
+  cudaMemset(ctx->d_scalars, 0, 16 * sizeof(int32_t));
+  cudaMemset(ctx->sort_small, 0, (256 + 16) * sizeof(uint32_t));
+  memset(ctx->h_scalars, 0, 16 * sizeof(int32_t));
+  *out = ctx;
+  return GSB_OK;
+}
+
+GSB_API int gsb_destroy(gsb_ctx* ctx) {
+  if (!ctx) return GSB_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  void* bufs[] = {ctx->keys_a, ctx->keys_b, ctx->vals_a, ctx->vals_b, ctx->sort_table, ctx->sort_small, ctx->scan_sums,
+                  ctx->tiles_touched, ctx->dcov3d, ctx->d_scalars};
+  for (void* p : bufs)
+    if (p) cudaFree(p);
+  if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+  delete ctx;
+  return GSB_OK;
+}
+
+GSB_API const char* gsb_last_error_string(gsb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+GSB_API int64_t gsb_launch_count(gsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+GSB_API int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered) {
+  if (!ctx) return GSB_ERR_INVALID;
+  return gsb_reserve_binning(ctx, (cudaStream_t)s, num_rendered);
+}
+
+// tuning knobs (not part of the reference surface): "blend_fwd_ppt", "blend_bwd_ppt" in {1,2,4,8}
+GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
+  if (!name) return GSB_ERR_INVALID;
+  bool ok = (value == 1 || value == 2 || value == 4 || value == 8);
+  if (!strcmp(name, "blend_fwd_ppt") && ok) {
+    g_blend_fwd_ppt = value;
+    return GSB_OK;
+  }
+  if (!strcmp(name, "blend_bwd_ppt") && ok) {
+    g_blend_bwd_ppt = value;
+    return GSB_OK;
+  }
+  return gsb_set_error(ctx, GSB_ERR_INVALID, "unknown option %s=%d", name, value);
+}
+
+static int key_bits_for(int num_tiles) {
+  int tb = 0;
+  while ((1 << tb) < num_tiles) ++tb;
+  return 32 + (tb < 1 ? 1 : tb);
+}
+
+GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
+                        const float* scales, const float* rotations, const float* opacities, const float* shs,
+                        int32_t* radii, int32_t* point_offsets, float* points_xy, float* depths, float* rgb,
+                        float* cov3Ds, float* conic_opacity, float* clamped_state, int32_t* point_list,
+                        int64_t point_list_capacity, int32_t* ranges, float* image, float* inv_depth, float* final_T,
+                        int32_t* n_contrib, int64_t* num_rendered_host) {
+  if (!ctx) return GSB_ERR_INVALID;
+  GSB_REQUIRE(ctx, f && n >= 0 && f->width > 0 && f->height > 0, "gsb_forward: bad frame or n");
+  cudaStream_t s = (cudaStream_t)s_;
+  const int gx = (f->width + kTile - 1) / kTile, gy = (f->height + kTile - 1) / kTile;
+  const int num_tiles = gx * gy;
+  const size_t pixels = (size_t)f->width * f->height;
+  int rc;
+  if ((rc = reserve_per_gaussian(ctx, s, n)) != GSB_OK) return rc;
+
+  // forward.py:719-752
+  rc = gsb_preprocess(ctx, s_, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds, rgb,
+                      conic_opacity, ctx->tiles_touched, clamped_state);
+  if (rc != GSB_OK) return rc;
+  // forward.py:755-764 (inclusive scan + the one host read-back of the frame)
+  int64_t D = 0;
+  rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, &D);
+  if (rc != GSB_OK) return rc;
+  if (num_rendered_host) *num_rendered_host = D;
+  if (D > (1LL << 30))  // forward.py:765-767
+    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "Number of rendered points exceeds the maximum supported by Warp.");
+  if (D > GSB_MAX_RENDERED)
+    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "num_rendered == 2^30 is not supported by the radix sort (max 2^30-1)");
+  if (D > point_list_capacity)
+    return gsb_set_error(ctx, GSB_ERR_CAPACITY, "point_list capacity %lld < num_rendered %lld",
+                         (long long)point_list_capacity, (long long)D);
+
+  if (D == 0) {
+    // forward.py:830: nothing is launched; every image-shaped output keeps its wp.zeros() state
+    GSB_CUDA(ctx, cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, s));
+    GSB_CUDA(ctx, cudaMemsetAsync(image, 0, sizeof(float) * 3 * pixels, s));
+    GSB_CUDA(ctx, cudaMemsetAsync(inv_depth, 0, sizeof(float) * pixels, s));
+    GSB_CUDA(ctx, cudaMemsetAsync(final_T, 0, sizeof(float) * pixels, s));
+    GSB_CUDA(ctx, cudaMemsetAsync(n_contrib, 0, sizeof(int32_t) * pixels, s));
+    return GSB_OK;
+  }
+  if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+  // forward.py:776-788
+  rc = gsb_duplicate_with_keys(ctx, s_, f->width, f->height, n, points_xy, depths, point_offsets, radii, D, ctx->keys_a,
+                               ctx->vals_a);
+  if (rc != GSB_OK) return rc;
+  // forward.py:791-824; the final pass writes the sorted values straight into point_list
+  bool in_b = false;
+  rc = gsb_radix_sort_pingpong(ctx, s, ctx->keys_a, ctx->vals_a, ctx->keys_b, ctx->vals_b, point_list, D, 0,
+                               key_bits_for(num_tiles), &in_b);
+  if (rc != GSB_OK) return rc;
+  const int64_t* sorted_keys = in_b ? ctx->keys_b : ctx->keys_a;
+  // forward.py:832-840
+  if ((rc = gsb_tile_ranges(ctx, s_, D, sorted_keys, num_tiles, ranges)) != GSB_OK) return rc;
+  // forward.py:844-863 (+ the no-op track_pixel_stats of 867-879)
+  return gsb_blend_forward(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
+                           final_T, n_contrib);
+}
+
+GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
+                         const float* opacities, const float* shs, const float* scales, const float* rotations,
+                         const int32_t* radii, const float* points_xy, const float* conic_opacity, const float* rgb,
+                         const float* clamped_state, const float* cov3Ds, const int32_t* point_list,
+                         const int32_t* ranges, const float* final_T, const int32_t* n_contrib,
+                         const float* dL_dpixels, float* dL_dmean3D, float* dL_dcolor, float* dL_dshs,
+                         float* dL_dopacity, float* dL_dscale, float* dL_drot, float* dL_dmean2D, float* dL_dconic,
+                         float* dL_dcov3D) {
+  (void)opacities;  // converted and unused by the reference as well (backward.py:1056)
+  if (!ctx) return GSB_ERR_INVALID;
+  GSB_REQUIRE(ctx, f && n >= 0, "gsb_backward: bad frame or n");
+  cudaStream_t s = (cudaStream_t)s_;
+  if (n == 0) return GSB_OK;
+  int rc;
+  if ((rc = reserve_per_gaussian(ctx, s, n)) != GSB_OK) return rc;
+  // backward.py:1135-1152
+  rc = gsb_blend_backward(ctx, s_, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
+                          dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+  if (rc != GSB_OK) return rc;
+  // backward.py:1155-1182
+  rc = gsb_preprocess_backward(ctx, s_, f, n, means, radii, shs, scales, rotations, cov3Ds, clamped_state, dL_dmean2D,
+                               dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, dL_drot, nullptr);
+  if (rc != GSB_OK) return rc;
+  // backward.py:1119,1195: the returned dL_dcov3D is a fresh zero buffer no kernel writes
+  if (dL_dcov3D) GSB_CUDA(ctx, cudaMemsetAsync(dL_dcov3D, 0, sizeof(float) * 6 * (size_t)n, s));
+  return GSB_OK;
+}

@@ -1,0 +1,147 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the CPU oracle and against the golden
+vectors generated from the reference's own source.  Integer / index outputs must be bit-exact;
+images, depths and per-Gaussian floats within the stated fp32 tolerances; gradients rel 1e-3."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ["radii", "point_offsets", "point_list", "ranges", "n_contrib"]
+FLOAT_KEYS = ["points_xy_image", "depths", "colors", "cov3Ds", "conic_opacity", "final_Ts", "clamped_state"]
+GRAD_KEYS = ["dL_dmean3D", "dL_dcolor", "dL_dshs", "dL_dopacity", "dL_dscale", "dL_drot", "dL_dmean2D", "dL_dconic",
+             "dL_dcov3D"]
+IMAGE_ATOL = 1e-4     # north_star: max abs 1e-4 on images
+GRAD_RTOL = 1e-3      # north_star: rel 1e-3 on gradients (norm-wise per tensor)
+
+
+@pytest.fixture(scope="module")
+def gs():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gsb200  # noqa: F401
+    from gsb200 import backward, forward, scene
+    import types
+    return types.SimpleNamespace(forward=forward, backward=backward, scene=scene)
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+
+
+def check_forward(got, want, what=""):
+    img, depth, buf = got
+    o_img, o_depth, o_buf = want
+    for k in INT_KEYS:
+        a, b = _np(buf[k]).reshape(o_buf[k].shape), o_buf[k]
+        assert np.array_equal(a, b), f"{what}{k}: {np.count_nonzero(a != b)} of {b.size} entries differ"
+    for k in FLOAT_KEYS:
+        a, b = _np(buf[k]).reshape(o_buf[k].shape), o_buf[k]
+        assert np.array_equal(a, b) or np.allclose(a, b, rtol=1e-5, atol=1e-6), f"{what}{k}"
+    assert np.abs(_np(img) - o_img).max() <= IMAGE_ATOL, what + "image"
+    assert np.abs(_np(depth) - o_depth).max() <= IMAGE_ATOL * max(1.0, np.abs(o_depth).max()), what + "depth"
+
+
+def check_grads(g, og, what=""):
+    assert set(g) == set(GRAD_KEYS)
+    for k in GRAD_KEYS:
+        a = _np(g[k]).reshape(og[k].shape).astype(np.float64)
+        b = og[k].astype(np.float64)
+        err = np.linalg.norm(a - b)
+        ref = np.linalg.norm(b)
+        assert err <= GRAD_RTOL * ref + 1e-12, f"{what}{k}: rel err {err / max(ref, 1e-30):.3e}"
+        assert np.isfinite(a).all(), k
+
+
+def _golden_kwargs(g):
+    return dict(background=g["in_bg"], means3D=g["in_means"], colors=None, opacity=g["in_opac"],
+                scales=g["in_scales"], rotations=g["in_rot"], scale_modifier=float(g["in_scale_modifier"]),
+                viewmatrix=g["in_view"], projmatrix=g["in_proj"], tan_fovx=float(g["in_tan_fovx"]),
+                tan_fovy=float(g["in_tan_fovy"]), image_height=int(g["in_H"]), image_width=int(g["in_W"]),
+                sh=g["in_sh"], degree=int(g["in_degree"]), campos=g["in_campos"], clamped=bool(g["in_clamped"]))
+
+
+@pytest.mark.parametrize("name", ["ref_lego_small", "ref_lego_deg1", "ref_lego_bg", "ref_example_96"])
+def test_golden_from_reference_source(gs, golden_dir, name):
+    """Forward + backward on the inputs of tests/golden/*.npz, compared with the arrays the
+    reference's own kernels produced under the Warp shim."""
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    img, depth, buf = gs.forward.render_gaussians(**_golden_kwargs(g))
+    want = {k[4:]: v for k, v in g.items() if k.startswith("fwd_")}
+    assert set(buf) == set(want)
+    check_forward((img, depth, buf), (g["image"], g["depth"], want), name + ": ")
+    if int(g["ref_bwd_oob"]):
+        return
+    grads = gs.backward.backward(
+        background=g["in_bg"], means3D=g["in_means"], dL_dpixels=g["dL_dpixels"], opacity=g["in_opac"],
+        shs=g["in_sh"], scales=g["in_scales"], rotations=g["in_rot"], scale_modifier=float(g["in_scale_modifier"]),
+        viewmatrix=g["in_view"], projmatrix=g["in_proj"], tan_fovx=float(g["in_tan_fovx"]),
+        tan_fovy=float(g["in_tan_fovy"]), image_height=int(g["in_H"]), image_width=int(g["in_W"]),
+        campos=g["in_campos"], radii=buf["radii"], means2D=buf["points_xy_image"],
+        conic_opacity=buf["conic_opacity"], rgb=buf["colors"], cov3Ds=buf["cov3Ds"], clamped=buf["clamped_state"],
+        geom_buffer={"radii": buf["radii"], "means2D": buf["points_xy_image"], "conic_opacity": buf["conic_opacity"],
+                     "rgb": buf["colors"], "clamped_state": buf["clamped_state"]},
+        binning_buffer={"point_list": buf["point_list"]},
+        img_buffer={"ranges": buf["ranges"], "final_Ts": buf["final_Ts"], "n_contrib": buf["n_contrib"]},
+        degree=int(g["in_degree"]))
+    check_grads(grads, {k[4:]: v for k, v in g.items() if k.startswith("bwd_")}, name + ": ")
+
+
+def test_example_scene_config1(gs, oracle):
+    """BASELINE config 1: render.py's 3-Gaussian scene at 1800x1800, pixel-wise vs the oracle."""
+    kw = gs.scene.example_render_kwargs()
+    got = gs.forward.render_gaussians(**kw)
+    want = oracle.render_gaussians(**kw)
+    check_forward(got, want, "C1: ")
+    assert _np(got[2]["radii"]).tolist() == [542, 485, 542]
+    assert got[2]["point_list"].numel() == 11779
+
+
+@pytest.mark.parametrize("n,w,h,smin,smax,ppt", [(3000, 100, 70, 0.01, 0.08, 1), (20000, 320, 240, 0.005, 0.05, 2),
+                                                 (20000, 333, 251, 0.005, 0.05, 4), (8000, 256, 256, 0.01, 0.1, 8)])
+def test_synthetic_forward_backward_vs_oracle(gs, oracle, n, w, h, smin, smax, ppt):
+    from gsb200 import _lib
+    _lib.context().set_option("blend_fwd_ppt", ppt)
+    _lib.context().set_option("blend_bwd_ppt", ppt)
+    try:
+        params, cam, target = gs.scene.synthetic_scene(n, w, h, smin, smax, seed=n + w)
+        kw = gs.scene.render_kwargs(params, cam)
+        got = gs.forward.render_gaussians(**kw)
+        oracle.set_threads(oracle.max_threads())
+        want = oracle.render_gaussians(**kw)
+        check_forward(got, want)
+        dpix = oracle.compute_image_gradients(want[0], target, lambda_dssim=0)
+        grads = gs.backward.backward(**gs.scene.backward_kwargs(params, cam, got[2], dpix))
+        oracle.set_threads(1)        # serial: deterministic accumulation order in the checker
+        ograds = oracle.backward(**gs.scene.backward_kwargs(params, cam, want[2], dpix))
+        check_grads(grads, ograds)
+    finally:
+        oracle.set_threads(1)
+        _lib.context().set_option("blend_fwd_ppt", 1)
+        _lib.context().set_option("blend_bwd_ppt", 1)
+
+
+def test_nothing_visible_gives_zero_image(gs, oracle):
+    """forward.py:830: when no Gaussian is rendered the image is all ZEROS, not background."""
+    params, cam, _ = gs.scene.synthetic_scene(500, 64, 48, 0.01, 0.05)
+    params["positions"] = params["positions"] + np.float32(100.0) * cam["camera_center"].astype(np.float32)
+    kw = gs.scene.render_kwargs(params, cam, background=(0.3, 0.6, 0.9))
+    img, depth, buf = gs.forward.render_gaussians(**kw)
+    o = oracle.render_gaussians(**kw)
+    assert buf["point_list"].numel() == 0 and o[2]["point_list"].size == 0
+    assert not _np(img).any() and not o[0].any()
+    check_forward((img, depth, buf), o)
+
+
+def test_torch_inputs_and_column_opacity(gs, oracle):
+    """Accepts torch tensors on any device and (N,1) opacities / (N,16,3) SH like to_warp_array."""
+    params, cam, _ = gs.scene.synthetic_scene(2000, 96, 64, 0.01, 0.06, seed=5)
+    kw = gs.scene.render_kwargs(params, cam)
+    kw_t = dict(kw)
+    kw_t["means3D"] = torch.from_numpy(params["positions"]).cuda()
+    kw_t["opacity"] = torch.from_numpy(params["opacities"]).reshape(-1, 1)
+    kw_t["sh"] = torch.from_numpy(params["shs"]).reshape(-1, 16, 3)
+    kw_t["background"] = torch.zeros(3)
+    check_forward(gs.forward.render_gaussians(**kw_t), oracle.render_gaussians(**kw))

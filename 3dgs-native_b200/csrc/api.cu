@@ -9,8 +9,17 @@
 
 int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* v0, int64_t* k1, int32_t* v1,
                             int32_t* final_vals, int64_t n, int begin_bit, int end_bit, bool* result_in_second);
+int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
+                           const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
+                           int64_t* num_rendered_host, int* max_count_host);
+int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
+                          const float* depths, const int32_t* radii, const int32_t* point_offsets,
+                          const int32_t* ranges, int64_t num_rendered, int max_count, int32_t* point_list);
+int gsb_tile_binning_max();
+int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
 extern int g_blend_fwd_ppt;
 extern int g_blend_bwd_ppt;
+int g_blend_cull = 1;
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -109,7 +118,7 @@ GSB_API int gsb_destroy(gsb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   void* bufs[] = {ctx->keys_a, ctx->keys_b, ctx->vals_a, ctx->vals_b, ctx->sort_table, ctx->sort_small, ctx->scan_sums,
-                  ctx->tiles_touched, ctx->dcov3d, ctx->d_scalars};
+                  ctx->tiles_touched, ctx->dcov3d, ctx->d_scalars, ctx->tile_count};
   for (void* p : bufs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -128,13 +137,21 @@ GSB_API int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered) {
 // tuning knobs (not part of the reference surface): "blend_fwd_ppt", "blend_bwd_ppt" in {1,2,4,8}
 GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
   if (!name) return GSB_ERR_INVALID;
-  bool ok = (value == 1 || value == 2 || value == 4 || value == 8);
+  const bool ok = (value == 1 || value == 2 || value == 4 || value == 8);
   if (!strcmp(name, "blend_fwd_ppt") && ok) {
     g_blend_fwd_ppt = value;
     return GSB_OK;
   }
   if (!strcmp(name, "blend_bwd_ppt") && ok) {
     g_blend_bwd_ppt = value;
+    return GSB_OK;
+  }
+  if (!strcmp(name, "binning") && (value == 0 || value == 1)) {
+    g_binning = value;
+    return GSB_OK;
+  }
+  if (!strcmp(name, "blend_cull") && (value == 0 || value == 1)) {
+    g_blend_cull = value;
     return GSB_OK;
   }
   return gsb_set_error(ctx, GSB_ERR_INVALID, "unknown option %s=%d", name, value);
@@ -165,10 +182,20 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   rc = gsb_preprocess(ctx, s_, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds, rgb,
                       conic_opacity, ctx->tiles_touched, clamped_state);
   if (rc != GSB_OK) return rc;
-  // forward.py:755-764 (inclusive scan + the one host read-back of the frame)
-  int64_t D = 0;
-  rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, &D);
+  // forward.py:755-764: inclusive scan (an output of the operator).  The one host read-back of the
+  // frame (num_rendered, and the longest tile list) comes from the per-tile counting pass below.
+  rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr);
   if (rc != GSB_OK) return rc;
+  int64_t D = 0;
+  int max_count = 0;
+  rc = gsb_tile_binning_count(ctx, s, n, f->width, f->height, points_xy, radii, point_offsets, ranges, &D, &max_count);
+  if (rc != GSB_OK) return rc;
+  if (D > ctx->bin_cap && D <= GSB_MAX_RENDERED) {
+    // first frame / scene grew: the rank buffer was too small.  Grow and redo the counting pass.
+    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+    rc = gsb_tile_binning_count(ctx, s, n, f->width, f->height, points_xy, radii, point_offsets, ranges, &D, &max_count);
+    if (rc != GSB_OK) return rc;
+  }
   if (num_rendered_host) *num_rendered_host = D;
   if (D > (1LL << 30))  // forward.py:765-767
     return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "Number of rendered points exceeds the maximum supported by Warp.");
@@ -180,26 +207,33 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
 
   if (D == 0) {
     // forward.py:830: nothing is launched; every image-shaped output keeps its wp.zeros() state
-    GSB_CUDA(ctx, cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, s));
+    // (ranges were already written as all (0,0) by the counting pass)
     GSB_CUDA(ctx, cudaMemsetAsync(image, 0, sizeof(float) * 3 * pixels, s));
     GSB_CUDA(ctx, cudaMemsetAsync(inv_depth, 0, sizeof(float) * pixels, s));
     GSB_CUDA(ctx, cudaMemsetAsync(final_T, 0, sizeof(float) * pixels, s));
     GSB_CUDA(ctx, cudaMemsetAsync(n_contrib, 0, sizeof(int32_t) * pixels, s));
     return GSB_OK;
   }
-  if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
-  // forward.py:776-788
-  rc = gsb_duplicate_with_keys(ctx, s_, f->width, f->height, n, points_xy, depths, point_offsets, radii, D, ctx->keys_a,
-                               ctx->vals_a);
-  if (rc != GSB_OK) return rc;
-  // forward.py:791-824; the final pass writes the sorted values straight into point_list
-  bool in_b = false;
-  rc = gsb_radix_sort_pingpong(ctx, s, ctx->keys_a, ctx->vals_a, ctx->keys_b, ctx->vals_b, point_list, D, 0,
-                               key_bits_for(num_tiles), &in_b);
-  if (rc != GSB_OK) return rc;
-  const int64_t* sorted_keys = in_b ? ctx->keys_b : ctx->keys_a;
-  // forward.py:832-840
-  if ((rc = gsb_tile_ranges(ctx, s_, D, sorted_keys, num_tiles, ranges)) != GSB_OK) return rc;
+  if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
+    // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
+    rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, point_offsets, ranges, D,
+                               max_count, point_list);
+    if (rc != GSB_OK) return rc;
+  } else {
+    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+    // forward.py:776-788
+    rc = gsb_duplicate_with_keys(ctx, s_, f->width, f->height, n, points_xy, depths, point_offsets, radii, D, ctx->keys_a,
+                                 ctx->vals_a);
+    if (rc != GSB_OK) return rc;
+    // forward.py:791-824; the final pass writes the sorted values straight into point_list
+    bool in_b = false;
+    rc = gsb_radix_sort_pingpong(ctx, s, ctx->keys_a, ctx->vals_a, ctx->keys_b, ctx->vals_b, point_list, D, 0,
+                                 key_bits_for(num_tiles), &in_b);
+    if (rc != GSB_OK) return rc;
+    const int64_t* sorted_keys = in_b ? ctx->keys_b : ctx->keys_a;
+    // forward.py:832-840
+    if ((rc = gsb_tile_ranges(ctx, s_, D, sorted_keys, num_tiles, ranges)) != GSB_OK) return rc;
+  }
   // forward.py:844-863 (+ the no-op track_pixel_stats of 867-879)
   return gsb_blend_forward(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
                            final_T, n_contrib);

@@ -1,0 +1,234 @@
+// blend_bwd.cu -- back-to-front replay of the tile blend: replaces wp_render_backward_kernel
+// (reference backward.py:558-706).  See blend.cu for the design notes shared with the forward.
+//
+// This translation unit is compiled with -fmad=true: gradients are compared with a tolerance
+// (rel 1e-3), so the gradient arithmetic may contract to FMAs and use one reciprocal instead of two
+// IEEE divisions.  Everything that feeds a DECISION (the Gaussian exponent, the exponential, the
+// alpha tests) goes through gs_power / gs_expf, which round every operation explicitly and are
+// therefore identical to the forward's and the oracle's no matter how this file is compiled.
+#include "blend_common.cuh"
+
+namespace {
+
+// Sum v[0..8] over the 32 lanes and add the totals into the four gradient arrays of Gaussian gid.
+__device__ __forceinline__ void warp_reduce9_red(float v[9], int lane, int gid, float* __restrict__ dL_dmean2D,
+                                                 float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+                                                 float* __restrict__ dL_dcolor) {
+  const unsigned full = 0xffffffffu;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = h16 ? v[i] : v[i + 4];
+    float keep = h16 ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(full, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = h8 ? v[i] : v[i + 2];
+    float keep = h8 ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(full, send, 8);
+  }
+  float send = h4 ? v[0] : v[1];
+  float keep = h4 ? v[1] : v[0];
+  float s = keep + __shfl_xor_sync(full, send, 4);
+  s += __shfl_xor_sync(full, s, 2);
+  s += __shfl_xor_sync(full, s, 1);
+  float o = v[8];
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) o += __shfl_xor_sync(full, o, m);
+
+  // lanes 0,4,...,28 hold value index 4*h16 + 2*h8 + h4; lane 1 takes the opacity
+  const int idx = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+  if ((lane & 3) == 0) {
+    float* dst;
+    if (idx < 3) dst = dL_dcolor + 3 * (size_t)gid + idx;              // r, g, b
+    else if (idx < 5) dst = dL_dmean2D + 3 * (size_t)gid + (idx - 3);  // x, y
+    else dst = dL_dconic + 4 * (size_t)gid + (idx == 7 ? 3 : idx - 5); // a, b, (0), c
+    atomicAdd(dst, s);
+  } else if (lane == 1) {
+    atomicAdd(dL_dopacity + gid, o);
+  }
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(256 / PPT, PPT == 1 ? 4 : 1)
+blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
+                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                      const float* __restrict__ rgb, const float* __restrict__ final_T,
+                      const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+                      float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+                      float* __restrict__ dL_dcolor) {
+  constexpr int NT = 256 / PPT;
+  constexpr int NW = NT / 32;
+  __shared__ float4 s_a[NT];  // x, y, conic.a, conic.b
+  __shared__ float4 s_b[NT];  // conic.c, opacity, power threshold, -
+  __shared__ float4 s_c[NT];  // r, g, b, gid (bits)
+  __shared__ int2 s_meta[NT]; // position in the tile's list, row mask
+  __shared__ int s_max[NW];
+  __shared__ int s_wcnt[NW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  const int tile_id = tile_y * P.grid_x + tile_x;
+  const int px = tile_x * kTile + (lane & 15);
+  const int row0 = tile_y * kTile + warp * (2 * PPT) + (lane >> 4);
+  const float pxf = (float)px;
+  const int2 range = ranges[tile_id];
+  const unsigned my_rows = ((1u << (2 * PPT)) - 1u) << (warp * 2 * PPT);
+  const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
+
+  float pyf[PPT], T[PPT], T_final[PPT], acc0[PPT], acc1[PPT], acc2[PPT], last_alpha[PPT], lc0[PPT], lc1[PPT], lc2[PPT];
+  float dp0[PPT], dp1[PPT], dp2[PPT], bgdot[PPT];
+  int kept[PPT];
+  int my_max = 0;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int py = row0 + 2 * k;
+    pyf[k] = (float)py;
+    const bool inside = (px < P.W && py < P.H);
+    const size_t pix = inside ? ((size_t)py * P.W + px) : 0;
+    T_final[k] = inside ? final_T[pix] : 0.0f;
+    T[k] = T_final[k];
+    // backward.py:619 last_kept = min(range_end, range_start + n_contrib), relative to range_start
+    kept[k] = inside ? min(range.y - range.x, n_contrib[pix]) : 0;
+    my_max = max(my_max, kept[k]);
+    dp0[k] = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
+    dp1[k] = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
+    dp2[k] = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
+    bgdot[k] = gs_dot3(P.bg0, P.bg1, P.bg2, dp0[k], dp1[k], dp2[k]);  // backward.py:679
+    acc0[k] = acc1[k] = acc2[k] = 0.0f;
+    last_alpha[k] = 0.0f;
+    lc0[k] = lc1[k] = lc2[k] = 0.0f;
+  }
+  my_max = __reduce_max_sync(0xffffffffu, my_max);
+  if (lane == 0) s_max[warp] = my_max;
+  __syncthreads();
+  int tile_max = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) tile_max = max(tile_max, s_max[w]);
+
+  const float ddelx_dx = 0.5f * (float)P.W;
+  const float ddely_dy = 0.5f * (float)P.H;
+
+  for (int hi = tile_max; hi > 0; hi -= NT) {
+    const int n_in = min(NT, hi);
+    __syncthreads();
+    float4 ea, eb, ec;
+    unsigned rowmask = 0u;
+    if (tid < n_in) {
+      const int gid = point_list[range.x + hi - 1 - tid];
+      const float2 p = xy[gid];
+      const float4 co = conic_opacity[gid];
+      const float thr = gs_power_threshold(co.w);
+      rowmask = P.cull ? gs_row_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffu;
+      ea = make_float4(p.x, p.y, co.x, co.y);
+      eb = make_float4(co.z, co.w, thr, 0.0f);
+      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
+    }
+    int cnt;
+    const int slot = compact_slot<NW>(rowmask != 0u, lane, warp, s_wcnt, cnt);
+    if (rowmask != 0u) {
+      s_a[slot] = ea;
+      s_b[slot] = eb;
+      s_c[slot] = ec;
+      s_meta[slot] = make_int2(hi - 1 - tid, (int)rowmask);
+    }
+    __syncthreads();
+    // a warp whose pixels all stopped before this batch has nothing to do in it
+    if (my_max <= hi - n_in) continue;
+    for (int j = 0; j < cnt; ++j) {
+      const int2 meta = s_meta[j];
+      const int pos = meta.x;      // position in the tile's list; pixel k replays it iff pos < kept[k]
+      if (pos >= my_max) continue; // warp-uniform
+      if (!((unsigned)meta.y & my_rows)) continue;  // warp-uniform
+      const float4 a = s_a[j];
+      const float4 b = s_b[j];
+      const float4 c = s_c[j];
+      const float dx = a.x - pxf;
+      float g[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) g[q] = 0.0f;
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (pos >= kept[k]) continue;
+        const float dy = a.y - pyf[k];
+        const float power = gs_power(a.z, a.w, b.x, dx, dy);
+        if (power > 0.0f) continue;  // backward.py:647
+        if (power < b.z) continue;   // provably alpha < 1/255
+        const float G = gs_expf(power);
+        const float alpha = f_min(0.99f, b.y * G);
+        if (alpha < (1.0f / 255.0f)) continue;  // backward.py:655
+        const float inv_1ma = 1.0f / (1.0f - alpha);   // backward.py:658,680 divide twice by (1 - alpha)
+        T[k] = T[k] * inv_1ma;
+        const float dchannel_dcolor = alpha * T[k];
+        acc0[k] = last_alpha[k] * lc0[k] + (1.0f - last_alpha[k]) * acc0[k];
+        acc1[k] = last_alpha[k] * lc1[k] + (1.0f - last_alpha[k]) * acc1[k];
+        acc2[k] = last_alpha[k] * lc2[k] + (1.0f - last_alpha[k]) * acc2[k];
+        lc0[k] = c.x;
+        lc1[k] = c.y;
+        lc2[k] = c.z;
+        float dL_dalpha = gs_dot3(c.x - acc0[k], c.y - acc1[k], c.z - acc2[k], dp0[k], dp1[k], dp2[k]);
+        g[0] += dchannel_dcolor * dp0[k];
+        g[1] += dchannel_dcolor * dp1[k];
+        g[2] += dchannel_dcolor * dp2[k];
+        dL_dalpha *= T[k];
+        last_alpha[k] = alpha;
+        dL_dalpha += (-T_final[k] * inv_1ma) * bgdot[k];
+        const float dL_dG = b.y * dL_dalpha;
+        const float gdx = G * dx;
+        const float gdy = G * dy;
+        const float dG_ddelx = -gdx * a.z - gdy * a.w;
+        const float dG_ddely = -gdy * b.x - gdx * a.w;
+        g[3] += dL_dG * dG_ddelx * ddelx_dx;
+        g[4] += dL_dG * dG_ddely * ddely_dy;
+        g[5] += -0.5f * gdx * dx * dL_dG;
+        g[6] += -0.5f * gdx * dy * dL_dG;
+        g[7] += -0.5f * gdy * dy * dL_dG;
+        g[8] += G * dL_dalpha;
+        any = true;
+      }
+      if (__any_sync(0xffffffffu, any))
+        warp_reduce9_red(g, lane, __float_as_int(c.w), dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+    }
+  }
+}
+
+template <int PPT>
+int launch_bwd(gsb_ctx* ctx, cudaStream_t s, const BlendParams& P, dim3 grid, const int32_t* ranges,
+               const int32_t* point_list, const float* xy, const float* conic_opacity, const float* rgb,
+               const float* final_T, const int32_t* n_contrib, const float* dL_dpixels, float* dL_dmean2D,
+               float* dL_dconic, float* dL_dopacity, float* dL_dcolor) {
+  GSB_LAUNCH(ctx, blend_backward_kernel<PPT>, grid, 256 / PPT, 0, s, P, reinterpret_cast<const int2*>(ranges),
+             point_list, reinterpret_cast<const float2*>(xy), reinterpret_cast<const float4*>(conic_opacity), rgb,
+             final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+  return GSB_OK;
+}
+
+}  // namespace
+
+int g_blend_bwd_ppt = 1;
+
+GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const int32_t* ranges,
+                               const int32_t* point_list, const float* points_xy, const float* conic_opacity,
+                               const float* rgb, const float* final_T, const int32_t* n_contrib,
+                               const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                               float* dL_dcolor) {
+  if (!ctx) return GSB_ERR_INVALID;
+  GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0 && n >= 0, "gsb_blend_backward: bad frame");
+  GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_backward: conic_opacity must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)s_;
+  if (n == 0) return GSB_OK;
+  GSB_CUDA(ctx, cudaMemsetAsync(dL_dmean2D, 0, sizeof(float) * 3 * (size_t)n, s));
+  GSB_CUDA(ctx, cudaMemsetAsync(dL_dconic, 0, sizeof(float) * 4 * (size_t)n, s));
+  GSB_CUDA(ctx, cudaMemsetAsync(dL_dopacity, 0, sizeof(float) * (size_t)n, s));
+  GSB_CUDA(ctx, cudaMemsetAsync(dL_dcolor, 0, sizeof(float) * 3 * (size_t)n, s));
+  BlendParams P = make_blend_params(f);
+  dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
+  switch (g_blend_bwd_ppt) {
+    case 2: return launch_bwd<2>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+    case 4: return launch_bwd<4>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+    case 8: return launch_bwd<8>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+    default: return launch_bwd<1>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+  }
+}

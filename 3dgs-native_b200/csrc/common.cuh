@@ -37,6 +37,9 @@ struct gsb_ctx {
   // generic scan scratch
   int32_t* scan_sums = nullptr;
   int64_t scan_cap = 0;
+  // tile-binning scratch: [num_tiles] counts + [num_tiles] write cursors
+  int32_t* tile_count = nullptr;
+  int64_t tile_cap = 0;
   // per-Gaussian internal buffers for gsb_forward / gsb_backward
   int32_t* tiles_touched = nullptr;
   float* dcov3d = nullptr;
@@ -49,6 +52,7 @@ struct gsb_ctx {
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...);
 int gsb_check_cuda(gsb_ctx* ctx, cudaError_t e, const char* what);
 int gsb_grow(gsb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_elems, size_t elem_size, cudaStream_t s);
+int gsb_reserve_binning(gsb_ctx* ctx, cudaStream_t s, int64_t num_rendered);
 
 #define GSB_CUDA(ctx, call)                                   \
   do {                                                        \

@@ -261,8 +261,6 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
   return GSB_OK;
 }
 
-int gsb_reserve_binning(gsb_ctx* ctx, cudaStream_t s, int64_t num_rendered);
-
 GSB_API int gsb_sort_pairs64(gsb_ctx* ctx, gsb_stream s_, int64_t* keys, int32_t* values, int64_t* tmp_keys,
                              int32_t* tmp_values, int64_t count, int begin_bit, int end_bit) {
   if (!ctx) return GSB_ERR_INVALID;

@@ -1,0 +1,268 @@
+// tilesort.cu -- the binning fast path of gsb_forward: an MSD/LSD hybrid of the reference's
+// "duplicate with keys -> radix sort of 64-bit tile|depth keys -> identify tile ranges"
+// (forward.py:517-586, 791-840) that produces the SAME point_list and ranges.
+//
+// The 64-bit key is (tile_id << 32) | depth_bits and the unsorted list is in ascending Gaussian
+// order, so the reference's stable sort orders the duplicates by (tile, depth_bits, gaussian_id).
+// Here the most significant digit -- the tile id -- is resolved by a counting sort:
+//   tile_count_kernel   one returning atomic per (Gaussian, tile) on a per-tile counter (one 128-byte
+//                       line per counter: neighbouring tiles must not serialise on one L2 line);
+//                       the returned arrival rank is stored at the duplicate's deterministic index
+//   tile_scan_kernel    exclusive scan of the counts = the tile ranges (and D, and the max count)
+//   tile_scatter_kernel every duplicate goes to slot start[tile] + rank as (depth_bits<<32 | id);
+//                       no atomics: the rank was recorded by the counting pass
+//   tile_sort_kernel    one CTA per tile sorts its segment (bitonic network on the 64-bit
+//                       composites -- they are unique, so any correct sort gives the stable order;
+//                       strides below 64 run in registers with shuffles, only the wide strides go
+//                       through shared memory) and writes the Gaussian ids to point_list
+// Traffic: 8 B written + 8 B read + 4 B written per duplicate, instead of 32 B per duplicate per
+// radix pass (6 passes at 800x800).  Tiles longer than kMaxTileSort fall back to the global radix
+// sort (sort.cu), which is also what the stage-level entry point gsb_sort_pairs64 runs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kCntStride = 32;  // ints between two tiles' counters = one 128-byte line each
+
+__global__ void __launch_bounds__(256)
+tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ radii,
+                  const int* __restrict__ point_offsets, int grid_x, int grid_y, int64_t capacity,
+                  int* __restrict__ tile_count, int* __restrict__ rank) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  int r = radii[tid];
+  if (r <= 0) return;
+  float2 p = xy[tid];
+  int rminx, rminy, rmaxx, rmaxy;
+  gs_get_rect(p.x, p.y, (float)r, (float)grid_x, (float)grid_y, rminx, rminy, rmaxx, rmaxy);
+  int64_t e = (tid > 0) ? point_offsets[tid - 1] : 0;  // index of this Gaussian's first duplicate
+  for (int y = rminy; y < rmaxy; ++y)
+    for (int x = rminx; x < rmaxx; ++x) {
+      const int k = atomicAdd(tile_count + (size_t)(y * grid_x + x) * kCntStride, 1);
+      if (e < capacity) rank[e] = k;
+      ++e;
+    }
+}
+
+// Single CTA: exclusive scan over the tiles.  Writes ranges (start,end) -- (0,0) for empty tiles,
+// like the zero-initialised reference buffer --, the per-tile write cursors, the total and the max.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __restrict__ ranges,
+                 int* __restrict__ out_total_max) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ int s_max[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  int my_max = 0;
+  __syncthreads();
+  for (int base = 0; base < num_tiles; base += 1024) {
+    const int i = base + tid;
+    const int c = (i < num_tiles) ? tile_count[(size_t)i * kCntStride] : 0;
+    my_max = max(my_max, c);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int wb = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      const int t = s_warp[w];
+      if (w < warp) wb += t;
+      tot += t;
+    }
+    const int start = s_carry + wb + inc - c;
+    if (i < num_tiles) {
+      ranges[i] = (c > 0) ? make_int2(start, start + c) : make_int2(0, 0);
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  my_max = __reduce_max_sync(0xffffffffu, my_max);
+  if (lane == 0) s_max[warp] = my_max;
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
+    out_total_max[0] = s_carry;
+    out_total_max[1] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
+                    const int* __restrict__ radii, const int* __restrict__ point_offsets, int grid_x, int grid_y,
+                    const int2* __restrict__ ranges, const int* __restrict__ rank,
+                    unsigned long long* __restrict__ binned) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  int r = radii[tid];
+  if (r <= 0) return;
+  float2 p = xy[tid];
+  int rminx, rminy, rmaxx, rmaxy;
+  gs_get_rect(p.x, p.y, (float)r, (float)grid_x, (float)grid_y, rminx, rminy, rmaxx, rmaxy);
+  const unsigned long long v = ((unsigned long long)__float_as_uint(depths[tid]) << 32) | (unsigned)tid;
+  int64_t e = (tid > 0) ? point_offsets[tid - 1] : 0;
+  for (int y = rminy; y < rmaxy; ++y)
+    for (int x = rminx; x < rmaxx; ++x) {
+      binned[ranges[y * grid_x + x].x + rank[e]] = v;
+      ++e;
+    }
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+  unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// One CTA per tile: bitonic sort of the segment's (depth_bits<<32 | id) composites.
+// A warp owns whole 64-element chunks (dealt round-robin); in chunk c lane l holds elements
+// e0 = 64c + l and e1 = e0 + 32.  Compare-exchange strides j < 32 are shuffles, j == 32 is
+// in-thread, j >= 64 goes through shared memory.  Direction of element i in merge size k:
+// ascending iff (i & k) == 0 (automatically true for the final merge k == n_pad).
+template <int CAP>
+__global__ void __launch_bounds__(256)
+tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
+                 int* __restrict__ point_list) {
+  extern __shared__ __align__(16) unsigned long long s_key[];
+  const int2 rg = ranges[blockIdx.x];
+  const int count = rg.y - rg.x;
+  if (count <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (count == 1) {
+    if (tid == 0) point_list[rg.x] = (int)(unsigned)binned[rg.x];
+    return;
+  }
+  int n_pad = 64;
+  while (n_pad < count) n_pad <<= 1;  // <= CAP by construction (host checked the max count)
+  const int chunks = n_pad >> 6;
+
+  // ---- phase 1: sort every 64-element chunk in registers (k = 2 .. 64)
+  for (int c = warp; c < chunks; c += 8) {
+    const int e0 = (c << 6) + lane, e1 = e0 + 32;
+    unsigned long long a = (e0 < count) ? binned[rg.x + e0] : ~0ull;
+    unsigned long long b = (e1 < count) ? binned[rg.x + e1] : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= 64; k <<= 1) {
+      const bool asc0 = (e0 & k) == 0, asc1 = (e1 & k) == 0;
+      if (k == 64 && ((a > b) == asc0)) {  // stride 32: the partner is this thread's other element
+        const unsigned long long t = a;
+        a = b;
+        b = t;
+      }
+#pragma unroll
+      for (int j = (k == 64 ? 16 : k >> 1); j > 0; j >>= 1) {
+        const unsigned long long pa = shfl_xor_u64(a, j), pb = shfl_xor_u64(b, j);
+        const bool lower = (lane & j) == 0;
+        a = ((a < pa) == (lower == asc0)) ? a : pa;  // lower half keeps the min when ascending
+        b = ((b < pb) == (lower == asc1)) ? b : pb;
+      }
+    }
+    s_key[e0] = a;
+    s_key[e1] = b;
+  }
+  // ---- phase 2: merges k = 128 .. n_pad; strides >= 64 through shared memory, the rest in registers
+  for (int k = 128; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j >= 64; j >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < (n_pad >> 1); i += 256) {
+        const int l = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        const int r = l + j;
+        const unsigned long long a = s_key[l], b = s_key[r];
+        if ((a > b) == ((l & k) == 0)) {
+          s_key[l] = b;
+          s_key[r] = a;
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = warp; c < chunks; c += 8) {
+      const int e0 = (c << 6) + lane, e1 = e0 + 32;
+      unsigned long long a = s_key[e0], b = s_key[e1];
+      const bool asc = (e0 & k) == 0;
+      if ((a > b) == asc) {
+        const unsigned long long t = a;
+        a = b;
+        b = t;
+      }
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const unsigned long long pa = shfl_xor_u64(a, j), pb = shfl_xor_u64(b, j);
+        const bool lower = (lane & j) == 0;
+        a = ((a < pa) == (lower == asc)) ? a : pa;
+        b = ((b < pb) == (lower == asc)) ? b : pb;
+      }
+      s_key[e0] = a;
+      s_key[e1] = b;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < count; i += 256) point_list[rg.x + i] = (int)(unsigned)s_key[i];
+}
+
+}  // namespace
+
+constexpr int kMaxTileSort = 16384;
+
+// Bins and sorts; on return *num_rendered_host and *max_count_host are set (one stream sync).
+// Returns GSB_OK with *used = false when the caller must fall back to the radix path (segment too
+// long) -- in that case nothing but the counts has been written.
+int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
+                           const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
+                           int64_t* num_rendered_host, int* max_count_host) {
+  const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+  const int num_tiles = gx * gy;
+  int rc = gsb_grow(ctx, (void**)&ctx->tile_count, &ctx->tile_cap, (int64_t)num_tiles * kCntStride, sizeof(int32_t), s);
+  if (rc != GSB_OK) return rc;
+  // The arrival ranks live in vals_a (one int per duplicate).  Its capacity is a guess until D is
+  // known (previous frame's D); if it turns out too small the caller re-runs this pass.
+  if (ctx->bin_cap == 0 && (rc = gsb_reserve_binning(ctx, s, 4 * (int64_t)n + 1024)) != GSB_OK) return rc;
+  int* tile_count = ctx->tile_count;
+  GSB_CUDA(ctx, cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)num_tiles * kCntStride, s));
+  if (n > 0)
+    GSB_LAUNCH(ctx, tile_count_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
+               radii, point_offsets, gx, gy, ctx->bin_cap, tile_count, ctx->vals_a);
+  GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, tile_count, reinterpret_cast<int2*>(ranges),
+             ctx->d_scalars + 4);
+  GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  GSB_CUDA(ctx, cudaStreamSynchronize(s));
+  const int32_t total = ctx->h_scalars[4];
+  *num_rendered_host = (total < 0) ? (int64_t)(uint32_t)total : (int64_t)total;
+  *max_count_host = ctx->h_scalars[5];
+  return GSB_OK;
+}
+
+int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
+                          const float* depths, const int32_t* radii, const int32_t* point_offsets,
+                          const int32_t* ranges, int64_t num_rendered, int max_count, int32_t* point_list) {
+  const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+  const int num_tiles = gx * gy;
+  // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
+  unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
+  const int2* rg = reinterpret_cast<const int2*>(ranges);
+  GSB_LAUNCH(ctx, tile_scatter_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
+             depths, radii, point_offsets, gx, gy, rg, ctx->vals_a, binned);
+  (void)num_rendered;
+  if (max_count <= 1024) {
+    GSB_LAUNCH(ctx, tile_sort_kernel<1024>, num_tiles, 256, 1024 * 8, s, rg, binned, point_list);
+  } else if (max_count <= 4096) {
+    GSB_LAUNCH(ctx, tile_sort_kernel<4096>, num_tiles, 256, 4096 * 8, s, rg, binned, point_list);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      GSB_CUDA(ctx, cudaFuncSetAttribute(tile_sort_kernel<kMaxTileSort>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kMaxTileSort * 8));
+      attr_set = true;
+    }
+    GSB_LAUNCH(ctx, tile_sort_kernel<kMaxTileSort>, num_tiles, 256, kMaxTileSort * 8, s, rg, binned, point_list);
+  }
+  return GSB_OK;
+}
+
+int gsb_tile_binning_max() { return kMaxTileSort; }

@@ -1,0 +1,343 @@
+"""The reference's step loop (train.py:920-1066) on GPU-resident state, plus view-batched data
+parallelism (BASELINE config 4).
+
+What the reference does per iteration and what happens here instead:
+
+* picks one random camera, decodes its PNG from disk, copies all parameters device->host->device
+  (train.py:928-955)              -> cameras are pre-packed ``gsb_frame`` structs, targets and
+                                     parameters stay in HBM
+* forward, L1 loss (2 read-backs), sign gradient, backward, 5 gradient copies (965-1051)
+                                  -> gsb_forward, fused L1 loss+gradient, gsb_backward writing
+                                     straight into the flat gradient buffer
+* adam_update(iteration) (1054)   -> one fused kernel over the flat buffers
+* densification_and_pruning(iteration) (1060, 351-713) -> same orchestration, same quirks
+
+Multi-GPU (not in the reference): a step's batch of views is split contiguously over the ranks,
+each rank sums the gradients of its views into one flat [59*N] buffer, ONE NCCL all-reduce sums
+the buffers, and every rank applies the identical Adam / densify step (replicas stay bit-identical
+because NCCL's result is the same on all ranks and clone/split noise is an index hash)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, optimizer
+from .config import GaussianParams
+from .scheduler import LRScheduler
+
+KEYS = ("positions", "scales", "rotations", "opacities", "shs")
+WIDTH = {"positions": 3, "scales": 3, "rotations": 4, "opacities": 1, "shs": 48}
+SHAPE = {"positions": lambda n: (n, 3), "scales": lambda n: (n, 3), "rotations": lambda n: (n, 4),
+         "opacities": lambda n: (n,), "shs": lambda n: (n * 16, 3)}
+
+
+class FlatGaussians:
+    """One contiguous fp32 buffer holding the five per-Gaussian tensors back to back (each segment
+    starts on a 16-byte boundary), with views of the reference's shapes.  The gradient instance of
+    this class is what gets all-reduced: one message of 59*N floats."""
+
+    def __init__(self, n: int, device, fill: float | None = 0.0):
+        self.n = n
+        offs, total = {}, 0
+        for k in KEYS:
+            offs[k] = total
+            total += (n * WIDTH[k] + 3) // 4 * 4
+        self.flat = (torch.zeros if fill == 0.0 else torch.empty)(max(total, 4), dtype=torch.float32, device=device)
+        self.views = {k: self.flat[offs[k]: offs[k] + n * WIDTH[k]].view(SHAPE[k](n)) for k in KEYS}
+
+    def __getitem__(self, k):
+        return self.views[k]
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def load(self, params: dict):
+        for k in KEYS:
+            self.views[k].copy_(_lib.to_device(params[k], device=self.flat.device).reshape(self.views[k].shape))
+        return self
+
+    def as_dict(self):
+        return dict(self.views)
+
+
+class FrameBuffers:
+    """Every per-view output of forward/backward, allocated once and reused across steps."""
+
+    def __init__(self, n: int, width: int, height: int, device, capacity: int):
+        f32, i32 = torch.float32, torch.int32
+        e = lambda *s, dtype=f32: torch.empty(s, dtype=dtype, device=device)  # noqa: E731
+        gx, gy = (width + 15) // 16, (height + 15) // 16
+        self.n, self.W, self.H = n, width, height
+        self.radii, self.point_offsets = e(n, dtype=i32), e(n, dtype=i32)
+        self.xy, self.depths, self.colors, self.cov3Ds = e(n, 2), e(n), e(n, 3), e(n, 6)
+        self.conic_opacity, self.clamped_state = e(n, 4), e(n, 3)
+        self.ranges = e(gx * gy, 2, dtype=i32)
+        self.final_T, self.n_contrib = e(height, width), e(height, width, dtype=i32)
+        self.image, self.depth = e(height, width, 3), e(height, width)
+        self.point_list = e(capacity, dtype=i32)
+        self.capacity = capacity
+        self.num_rendered = 0
+        self.dpix = e(height, width, 3)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        # backward scratch that is not a parameter gradient
+        self.dL_dcolor, self.dL_dmean2D, self.dL_dconic = e(n, 3), e(n, 3), e(n, 4)
+
+    def as_reference_dict(self):
+        """The 12-key dict of forward.py:881-894."""
+        return {"radii": self.radii, "point_offsets": self.point_offsets, "points_xy_image": self.xy,
+                "depths": self.depths, "colors": self.colors, "cov3Ds": self.cov3Ds,
+                "conic_opacity": self.conic_opacity, "point_list": self.point_list[: self.num_rendered],
+                "ranges": self.ranges, "final_Ts": self.final_T, "n_contrib": self.n_contrib,
+                "clamped_state": self.clamped_state}
+
+
+class Trainer:
+    def __init__(self, cameras, targets=None, num_points=None, params=None, config=None, device=None,
+                 rank=0, world_size=1, process_group=None):
+        self.config = GaussianParams.get_config_dict()
+        if config:
+            self.config.update(config)
+        self.ctx = _lib.context(device)
+        self.device = torch.device("cuda", self.ctx.device_index)
+        self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.cameras = cameras
+        bg = self.config["background_color"]
+        self.frames = [_lib.make_frame(c["world_to_camera"], c["full_proj_matrix"], c["camera_center"], c["tan_fovx"],
+                                       c["tan_fovy"], c["width"], c["height"], bg, self.config["sh_degree"], True,
+                                       self.config["scale_modifier"]) for c in cameras]
+        self.targets = None if targets is None else [_lib.to_device(t, device=self.device) for t in targets]
+        from .utils.camera_utils import scene_extent
+        self.scene_extent = scene_extent(cameras, self.config.get("camera_extent_factor", 1.0))
+        if params is not None:
+            n = int(np.asarray(params["positions"].shape)[0]) if not isinstance(params["positions"], torch.Tensor) \
+                else params["positions"].shape[0]
+            self.num_points = n
+            self.params = FlatGaussians(n, self.device).load(params)
+        else:
+            self.num_points = n = int(num_points or self.config["num_points"])
+            self.params = FlatGaussians(n, self.device)
+            optimizer.init_gaussian_params(self.params["positions"], self.params["scales"], self.params["rotations"],
+                                           self.params["opacities"], self.params["shs"], n, self.config["initial_scale"])
+        self._alloc_state()
+        sc = self.config["lr_scheduler_config"]
+        ff = sc["final_lr_factor"]
+        self.lr_scheduler = None
+        if self.config["use_lr_scheduler"]:
+            self.lr_scheduler = {k: LRScheduler(sc[k], ff) for k in ("lr_pos", "lr_scale", "lr_rot", "lr_sh", "lr_opac")}
+        self.fb = None
+        self.losses = []
+
+    # ---- state -------------------------------------------------------------------------------
+    def _alloc_state(self):
+        n = self.num_points
+        self.grads = FlatGaussians(n, self.device)      # train.py:160-164 (zeros)
+        self.adam_m = FlatGaussians(n, self.device)
+        self.adam_v = FlatGaussians(n, self.device)
+        self.grads_tmp = None
+        self.fb = None
+
+    def _frame_buffers(self, cam):
+        W, H = cam["width"], cam["height"]
+        fb = self.fb
+        if fb is None or fb.n != self.num_points or fb.W != W or fb.H != H:
+            cap = max(self.ctx.capacity_hint, 4 * self.num_points, 1024)
+            fb = self.fb = FrameBuffers(self.num_points, W, H, self.device, cap)
+        return fb
+
+    # ---- forward / backward on preallocated buffers ---------------------------------------------
+    def forward(self, cam_index: int) -> FrameBuffers:
+        """render_gaussians as called at train.py:935-955."""
+        cam, frame = self.cameras[cam_index], self.frames[cam_index]
+        fb = self._frame_buffers(cam)
+        P, p, L = self.params, _lib.ptr, _lib.lib()
+        D = C.c_int64(0)
+        for _ in range(2):
+            rc = L.gsb_forward(self.ctx.h, _lib.stream_ptr(self.ctx.device_index), C.byref(frame), self.num_points,
+                               p(P["positions"]), p(P["scales"]), p(P["rotations"]), p(P["opacities"]), p(P["shs"]),
+                               p(fb.radii), p(fb.point_offsets), p(fb.xy), p(fb.depths), p(fb.colors), p(fb.cov3Ds),
+                               p(fb.conic_opacity), p(fb.clamped_state), p(fb.point_list), fb.capacity, p(fb.ranges),
+                               p(fb.image), p(fb.depth), p(fb.final_T), p(fb.n_contrib), C.byref(D))
+            if rc == _lib.GSB_ERR_CAPACITY:
+                fb.capacity = int(D.value) + int(D.value) // 8 + 1024
+                fb.point_list = torch.empty(fb.capacity, dtype=torch.int32, device=self.device)
+                continue
+            self.ctx.check(rc)
+            break
+        fb.num_rendered = int(D.value)
+        self.ctx.capacity_hint = max(self.ctx.capacity_hint, fb.num_rendered + fb.num_rendered // 8)
+        return fb
+
+    def loss_and_pixel_gradients(self, fb: FrameBuffers, target):
+        """l1_loss + compute_image_gradients (train.py:965-979), fused; the loss stays on the device."""
+        H, W = fb.H, fb.W
+        l1_weight = (1.0 - 0.0) / (H * W * 3.0)          # train.py:978 passes lambda_dssim=0
+        self.ctx.check(_lib.lib().gsb_l1_loss_grad(self.ctx.h, _lib.stream_ptr(self.ctx.device_index), H * W * 3,
+                                                   _lib.ptr(fb.image), _lib.ptr(target), l1_weight, _lib.ptr(fb.dpix),
+                                                   _lib.ptr(fb.loss_sum)))
+
+    def backward(self, cam_index: int, fb: FrameBuffers, out: FlatGaussians):
+        """backward() as called at train.py:1006-1044; parameter gradients land in ``out``."""
+        frame, p = self.frames[cam_index], _lib.ptr
+        P = self.params
+        rc = _lib.lib().gsb_backward(
+            self.ctx.h, _lib.stream_ptr(self.ctx.device_index), C.byref(frame), self.num_points, p(P["positions"]),
+            p(P["opacities"]), p(P["shs"]), p(P["scales"]), p(P["rotations"]), p(fb.radii), p(fb.xy),
+            p(fb.conic_opacity), p(fb.colors), p(fb.clamped_state), p(fb.cov3Ds), p(fb.point_list), p(fb.ranges),
+            p(fb.final_T), p(fb.n_contrib), p(fb.dpix), p(out["positions"]), p(fb.dL_dcolor), p(out["shs"]),
+            p(out["opacities"]), p(out["scales"]), p(out["rotations"]), p(fb.dL_dmean2D), p(fb.dL_dconic), p(None))
+        self.ctx.check(rc)
+
+    # ---- one optimisation step -------------------------------------------------------------------
+    def learning_rates(self, iteration):
+        sc = self.config["lr_scheduler_config"]
+        if self.lr_scheduler:       # train.py:720-725
+            T = self.config["num_iterations"]
+            return {k: s.get_lr(iteration, T) for k, s in self.lr_scheduler.items()}
+        return {k: sc[k] for k in ("lr_pos", "lr_scale", "lr_rot", "lr_sh", "lr_opac")}
+
+    def optimizer_step(self, iteration):
+        """train.py:716-794."""
+        lr, G, P, M, V = self.learning_rates(iteration), self.grads, self.params, self.adam_m, self.adam_v
+        optimizer.adam_update(G["positions"], G["scales"], G["rotations"], G["opacities"], G["shs"], self.num_points,
+                              lr["lr_pos"], lr["lr_scale"], lr["lr_rot"], lr["lr_opac"], lr["lr_sh"],
+                              self.config["adam_beta1"], self.config["adam_beta2"], self.config["adam_epsilon"], iteration,
+                              P["positions"], P["scales"], P["rotations"], P["opacities"], P["shs"],
+                              M["positions"], M["scales"], M["rotations"], M["opacities"], M["shs"],
+                              V["positions"], V["scales"], V["rotations"], V["opacities"], V["shs"])
+
+    def accumulate_view(self, cam_index: int, target, first: bool):
+        """forward + loss gradient + backward of one view; gradients are written (first view) or
+        added (further views of the batch) into self.grads."""
+        fb = self.forward(cam_index)
+        self.loss_and_pixel_gradients(fb, target)
+        if first:
+            self.backward(cam_index, fb, self.grads)
+        else:
+            if self.grads_tmp is None or self.grads_tmp.n != self.num_points:
+                self.grads_tmp = FlatGaussians(self.num_points, self.device, fill=None)
+            self.backward(cam_index, fb, self.grads_tmp)
+            self.ctx.check(_lib.lib().gsb_accumulate_f32(self.ctx.h, _lib.stream_ptr(self.ctx.device_index),
+                                                         _lib.ptr(self.grads.flat), _lib.ptr(self.grads_tmp.flat),
+                                                         self.grads.flat.numel()))
+        return fb
+
+    def all_reduce_gradients(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def train_step(self, iteration: int, cam_indices, targets=None, densify=True):
+        """One step on a batch of views.  ``cam_indices`` is the GLOBAL batch; this rank takes the
+        contiguous slice [rank*B/G, (rank+1)*B/G).  With one view and one rank this is exactly one
+        iteration of the reference loop.  Returns the device tensor holding this rank's last
+        sum|render - target| (divide by 3HW for the reference's loss)."""
+        B = len(cam_indices)
+        per = B // self.world_size
+        assert per * self.world_size == B and per >= 1, "batch must be a multiple of the world size"
+        mine = range(self.rank * per, (self.rank + 1) * per)
+        fb = None
+        for j, b in enumerate(mine):
+            ci = cam_indices[b]
+            tgt = targets[b] if targets is not None else self.targets[ci]
+            fb = self.accumulate_view(ci, tgt, first=(j == 0))
+        self.all_reduce_gradients()
+        self.optimizer_step(iteration)
+        if densify:
+            self.densification_and_pruning(iteration)
+        return fb.loss_sum
+
+    # ---- densify / prune, train.py:351-713 ------------------------------------------------------
+    def _alloc_like(self, n):
+        return FlatGaussians(n, self.device)          # wp.zeros outputs of train.py:441-447 etc.
+
+    def _replace(self, new: FlatGaussians):
+        self.params, self.num_points = new, new.n
+        self._alloc_state()                            # train.py:474-476: grads, m, v all reset to zeros
+
+    def densification_and_pruning(self, iteration):
+        cfg = self.config
+        log = {"cloned": 0, "split": 0, "split_removed": 0, "pruned": 0, "opacity_reset": False}
+        i32 = torch.int32
+        if (iteration > cfg["densify_from_iter"] and iteration < cfg["densify_until_iter"]
+                and iteration % cfg["densification_interval"] == 0):
+            n = self.num_points
+            avg_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+            optimizer.compute_grad_norms(self.grads["positions"], avg_grads, n)
+            gt, pd, ext = cfg["densify_grad_threshold"], cfg["percent_dense"], self.scene_extent
+            P = self.params
+            clone_mask = torch.zeros(n, dtype=i32, device=self.device)
+            optimizer.mark_clone_candidates(avg_grads, P["scales"], gt, ext, pd, n, clone_mask)
+            clone_prefix = torch.zeros_like(clone_mask)
+            total_to_clone = optimizer.array_scan(clone_mask, clone_prefix, inclusive=False)
+            if total_to_clone > 0:
+                out = self._alloc_like(n + total_to_clone)
+                optimizer.clone_gaussians(clone_mask, clone_prefix, P["positions"], P["scales"], P["rotations"],
+                                          P["opacities"], P["shs"], 0.01, n, out["positions"], out["scales"],
+                                          out["rotations"], out["opacities"], out["shs"])
+                self._replace(out)
+                log["cloned"] = total_to_clone
+            n, P = self.num_points, self.params
+            split_mask = torch.zeros(n, dtype=i32, device=self.device)
+            # quirk G4: avg_grads still has the pre-clone length
+            optimizer.mark_split_candidates(avg_grads, P["scales"], gt, ext, pd, n, split_mask)
+            split_prefix = torch.zeros_like(split_mask)
+            total_to_split = optimizer.array_scan(split_mask, split_prefix, inclusive=False)
+            if total_to_split > 0:
+                N0, n_split = n, 2
+                new_n = N0 + total_to_split * n_split
+                out = self._alloc_like(new_n)
+                optimizer.split_gaussians(split_mask, split_prefix, P["positions"], P["scales"], P["rotations"],
+                                          P["opacities"], P["shs"], n_split, 0.8, N0, out["positions"], out["scales"],
+                                          out["rotations"], out["opacities"], out["shs"])
+                self._replace(out)
+                log["split"] = total_to_split
+                P = self.params
+                valid = torch.zeros(new_n, dtype=i32, device=self.device)
+                optimizer.split_valid_mask(split_mask, valid, N0, new_n)
+                prefix = torch.zeros_like(valid)
+                valid_count = optimizer.array_scan(valid, prefix, inclusive=False)
+                if valid_count < new_n:
+                    out = self._alloc_like(valid_count)
+                    optimizer.compact_gaussians(valid, prefix, P["positions"], P["scales"], P["rotations"],
+                                                P["opacities"], P["shs"], out["positions"], out["scales"],
+                                                out["rotations"], out["opacities"], out["shs"])
+                    log["split_removed"] = new_n - valid_count
+                    self._replace(out)
+            n, P = self.num_points, self.params
+            valid = torch.zeros(n, dtype=i32, device=self.device)
+            optimizer.prune_gaussians(P["opacities"], cfg["cull_opacity_threshold"], n, valid)
+            prefix = torch.zeros_like(valid)
+            valid_count = optimizer.array_scan(valid, prefix, inclusive=False)
+            prune_count = n - valid_count
+            prune_ratio = prune_count / n if n > 0 else 0
+            if (valid_count >= cfg["min_valid_points"] and valid_count <= cfg["max_valid_points"]
+                    and prune_ratio <= cfg["max_allowed_prune_ratio"] and valid_count < n):
+                out = self._alloc_like(valid_count)
+                optimizer.compact_gaussians(valid, prefix, P["positions"], P["scales"], P["rotations"], P["opacities"],
+                                            P["shs"], out["positions"], out["scales"], out["rotations"],
+                                            out["opacities"], out["shs"])
+                self._replace(out)
+                log["pruned"] = prune_count
+        background_is_white = all(c == 1.0 for c in cfg["background_color"])
+        if (iteration % cfg["opacity_reset_interval"] == 0
+                or (background_is_white and iteration == cfg["densify_from_iter"])):   # quirk G6: iteration 0 too
+            optimizer.reset_opacities(0.01, self.num_points, self.params["opacities"])
+            log["opacity_reset"] = True
+        return log
+
+    # ---- the reference's loop --------------------------------------------------------------------
+    def train(self, num_iterations=None, batch_size=1, seed=42, log_every=0):
+        """train.py:920-1066 with a seeded camera sampler; losses are read back every ``log_every``
+        steps only (the reference blocks on the loss every iteration)."""
+        T = num_iterations or self.config["num_iterations"]
+        rng = np.random.default_rng(seed)
+        for it in range(T):
+            cams = [int(rng.integers(0, len(self.cameras))) for _ in range(batch_size)]
+            loss_sum = self.train_step(it, cams)
+            if log_every and it % log_every == 0:
+                fb = self.fb
+                H, W = (fb.H, fb.W) if fb is not None else (1, 1)
+                self.losses.append((it, float(loss_sum.item()) / (3 * H * W), self.num_points))
+        return self.losses

@@ -1,0 +1,119 @@
+"""Stage-level GPU parity through the C ABI: prefix sum, duplicate-with-keys, the stable 64-bit radix
+sort, tile ranges, and the two binning paths of gsb_forward (bit-exact integer work)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gsb200  # noqa: F401
+    from gsb200 import _lib
+    return _lib
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 2048, 2049, 300000, 1234567])
+def test_prefix_sum(L, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 30, n).astype(np.int32)
+    ctx, s = L.context(), L.stream_ptr()
+    d_in, d_out = _cuda(a), torch.empty(n, dtype=torch.int32, device="cuda")
+    total = C.c_int64(0)
+    ctx.check(L.lib().gsb_scan_tiles(ctx.h, s, n, L.ptr(d_in), L.ptr(d_out), C.byref(total)))
+    want = np.cumsum(a, dtype=np.int64)
+    assert np.array_equal(d_out.cpu().numpy(), want.astype(np.int32))          # utils/wp_utils.py:46-60 (inclusive)
+    assert total.value == int(want[-1])
+    last = C.c_int32(0)
+    ctx.check(L.lib().gsb_scan_mask(ctx.h, s, n, L.ptr(d_in), L.ptr(d_out), C.byref(last)))
+    excl = want - a
+    assert np.array_equal(d_out.cpu().numpy(), excl.astype(np.int32))          # array_scan(inclusive=False)
+    assert last.value == int(excl[-1])                                         # quirk G5: last flag not counted
+
+
+@pytest.mark.parametrize("n,bits,distinct", [(1, 44, 0), (77, 44, 0), (4096, 44, 0), (4097, 47, 0), (200000, 44, 0),
+                                              (200000, 44, 37), (1 << 20, 64, 0), (300001, 40, 2)])
+def test_radix_sort_pairs_is_stable(L, n, bits, distinct):
+    """Ascending, STABLE (ties keep their input order) -- forward.py:799-803 [Warp]."""
+    rng = np.random.default_rng(n + bits)
+    if distinct:
+        keys = rng.integers(0, distinct, n).astype(np.int64) << 20          # massive ties
+    else:
+        keys = rng.integers(0, 1 << 62, n, dtype=np.int64) >> (62 - min(bits, 62))
+    if bits == 64:
+        keys = keys | (rng.integers(0, 2, n).astype(np.int64) << 62)
+    vals = np.arange(n, dtype=np.int32)
+    ctx, s = L.context(), L.stream_ptr()
+    dk, dv = _cuda(keys), _cuda(vals)
+    ctx.check(L.lib().gsb_sort_pairs64(ctx.h, s, L.ptr(dk), L.ptr(dv), None, None, n, 0, bits))
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(dk.cpu().numpy(), keys[order])
+    assert np.array_equal(dv.cpu().numpy(), vals[order])
+
+
+def _scene(n, w, h, smin, smax, seed):
+    import gsb200  # noqa: F401
+    from gsb200 import scene
+    params, cam, _ = scene.synthetic_scene(n, w, h, smin, smax, seed=seed, with_target=False)
+    return scene.render_kwargs(params, cam)
+
+
+def test_duplicate_keys_and_ranges_vs_oracle(L, oracle):
+    kw = _scene(15000, 200, 150, 0.005, 0.06, 3)
+    o_img, _, ob = oracle.render_gaussians(**kw, return_extra=True)
+    ctx, s = L.context(), L.stream_ptr()
+    D = ob["_num_rendered"]
+    xy, depths = _cuda(ob["points_xy_image"]), _cuda(ob["depths"])
+    offs, radii = _cuda(ob["point_offsets"]), _cuda(ob["radii"])
+    keys = torch.empty(D, dtype=torch.int64, device="cuda")
+    vals = torch.empty(D, dtype=torch.int32, device="cuda")
+    ctx.check(L.lib().gsb_duplicate_with_keys(ctx.h, s, 200, 150, 15000, L.ptr(xy), L.ptr(depths), L.ptr(offs),
+                                              L.ptr(radii), D, L.ptr(keys), L.ptr(vals)))
+    assert np.array_equal(keys.cpu().numpy(), ob["_keys_unsorted"])        # tile|depth keys, bit-exact
+    assert np.array_equal(vals.cpu().numpy(), ob["_vals_unsorted"])
+    gx, gy = (200 + 15) // 16, (150 + 15) // 16
+    bits = 32 + int(np.ceil(np.log2(gx * gy)))
+    ctx.check(L.lib().gsb_sort_pairs64(ctx.h, s, L.ptr(keys), L.ptr(vals), None, None, D, 0, bits))
+    assert np.array_equal(keys.cpu().numpy(), ob["_keys_sorted"])
+    assert np.array_equal(vals.cpu().numpy(), ob["point_list"])
+    ranges = torch.empty((gx * gy, 2), dtype=torch.int32, device="cuda")
+    ctx.check(L.lib().gsb_tile_ranges(ctx.h, s, D, L.ptr(keys), gx * gy, L.ptr(ranges)))
+    assert np.array_equal(ranges.cpu().numpy(), ob["ranges"])
+
+
+@pytest.mark.parametrize("n,w,h,smin,smax", [(20000, 320, 240, 0.005, 0.05),   # short lists  (<= 1024 per tile)
+                                              (6000, 64, 48, 0.1, 0.4),         # long lists   (> 1024 per tile)
+                                              (9000, 32, 32, 0.5, 1.5)])        # every Gaussian in every tile (> 4096)
+def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax):
+    """gsb_forward's per-tile counting sort + shared-memory sort and the global radix sort give the
+    same point_list / ranges / n_contrib as the oracle's stable sort (incl. exact depth ties)."""
+    import gsb200  # noqa: F401
+    from gsb200 import forward
+    kw = _scene(n, w, h, smin, smax, n)
+    kw["means3D"] = kw["means3D"].copy()
+    kw["means3D"][1::7] = kw["means3D"][0::7][: len(kw["means3D"][1::7])]     # duplicates => depth ties
+    oracle.set_threads(oracle.max_threads())
+    try:
+        o_img, _, ob = oracle.render_gaussians(**kw)
+    finally:
+        oracle.set_threads(1)
+    longest = int(np.diff(ob["ranges"], axis=1).max())
+    ctx = L.context()
+    for mode in (0, 1):
+        ctx.set_option("binning", mode)
+        try:
+            img, _, buf = forward.render_gaussians(**kw)
+        finally:
+            ctx.set_option("binning", 0)
+        for k in ("point_offsets", "point_list", "ranges", "n_contrib", "radii"):
+            assert np.array_equal(buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]), (mode, k, longest)
+        assert np.abs(img.cpu().numpy() - o_img).max() <= 1e-4

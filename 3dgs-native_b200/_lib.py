@@ -42,6 +42,7 @@ _SIGS = {
     "gsb_duplicate_with_keys": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp]),
     "gsb_sort_pairs64": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int]),
     "gsb_tile_ranges": (C.c_int, [vp, vp, i64, vp, i32, vp]),
+    "gsb_bin_by_tile": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, C.POINTER(i64), C.POINTER(i32)]),
     "gsb_blend_forward": (C.c_int, [vp, vp, C.POINTER(Frame)] + [vp] * 10),
     "gsb_forward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 14 + [i64] + [vp] * 5 + [C.POINTER(i64)]),
     "gsb_blend_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 12),

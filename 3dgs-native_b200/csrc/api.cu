@@ -163,6 +163,60 @@ static int key_bits_for(int num_tiles) {
   return 32 + (tb < 1 ? 1 : tb);
 }
 
+GSB_API int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s_, int32_t width, int32_t height, int32_t n,
+                            const float* points_xy, const float* depths, const int32_t* radii,
+                            const int32_t* point_offsets, int32_t* point_list, int64_t point_list_capacity,
+                            int32_t* ranges, int64_t* num_rendered_host, int32_t* used_tile_path_host) {
+  if (!ctx) return GSB_ERR_INVALID;
+  GSB_REQUIRE(ctx, n >= 0 && width > 0 && height > 0, "gsb_bin_by_tile: bad size");
+  cudaStream_t s = (cudaStream_t)s_;
+  const int num_tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+  int rc;
+  int64_t D = 0;
+  int max_count = 0;
+  rc = gsb_tile_binning_count(ctx, s, n, width, height, points_xy, radii, point_offsets, ranges, &D, &max_count);
+  if (rc != GSB_OK) return rc;
+  if (D > ctx->bin_cap && D <= GSB_MAX_RENDERED) {
+    // first frame / scene grew: the rank buffer was too small.  Grow and redo the counting pass.
+    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+    rc = gsb_tile_binning_count(ctx, s, n, width, height, points_xy, radii, point_offsets, ranges, &D, &max_count);
+    if (rc != GSB_OK) return rc;
+  }
+  if (num_rendered_host) *num_rendered_host = D;
+  if (used_tile_path_host) *used_tile_path_host = 0;
+  if (D > (1LL << 30))  // forward.py:765-767
+    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "Number of rendered points exceeds the maximum supported by Warp.");
+  if (D > GSB_MAX_RENDERED)
+    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "num_rendered == 2^30 is not supported by the radix sort (max 2^30-1)");
+  if (D > point_list_capacity)
+    return gsb_set_error(ctx, GSB_ERR_CAPACITY, "point_list capacity %lld < num_rendered %lld",
+                         (long long)point_list_capacity, (long long)D);
+
+  if (D == 0) return GSB_OK;  // ranges are all (0,0) already
+  if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
+    // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
+    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, point_offsets, ranges, D,
+                               max_count, point_list);
+    if (rc != GSB_OK) return rc;
+    if (used_tile_path_host) *used_tile_path_host = 1;
+  } else {
+    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+    // forward.py:776-788
+    rc = gsb_duplicate_with_keys(ctx, s_, width, height, n, points_xy, depths, point_offsets, radii, D, ctx->keys_a,
+                                 ctx->vals_a);
+    if (rc != GSB_OK) return rc;
+    // forward.py:791-824; the final pass writes the sorted values straight into point_list
+    bool in_b = false;
+    rc = gsb_radix_sort_pingpong(ctx, s, ctx->keys_a, ctx->vals_a, ctx->keys_b, ctx->vals_b, point_list, D, 0,
+                                 key_bits_for(num_tiles), &in_b);
+    if (rc != GSB_OK) return rc;
+    const int64_t* sorted_keys = in_b ? ctx->keys_b : ctx->keys_a;
+    // forward.py:832-840
+    if ((rc = gsb_tile_ranges(ctx, s_, D, sorted_keys, num_tiles, ranges)) != GSB_OK) return rc;
+  }
+  return GSB_OK;
+}
+
 GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
                         const float* scales, const float* rotations, const float* opacities, const float* shs,
                         int32_t* radii, int32_t* point_offsets, float* points_xy, float* depths, float* rgb,
@@ -187,24 +241,10 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr);
   if (rc != GSB_OK) return rc;
   int64_t D = 0;
-  int max_count = 0;
-  rc = gsb_tile_binning_count(ctx, s, n, f->width, f->height, points_xy, radii, point_offsets, ranges, &D, &max_count);
-  if (rc != GSB_OK) return rc;
-  if (D > ctx->bin_cap && D <= GSB_MAX_RENDERED) {
-    // first frame / scene grew: the rank buffer was too small.  Grow and redo the counting pass.
-    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
-    rc = gsb_tile_binning_count(ctx, s, n, f->width, f->height, points_xy, radii, point_offsets, ranges, &D, &max_count);
-    if (rc != GSB_OK) return rc;
-  }
+  rc = gsb_bin_by_tile(ctx, s_, f->width, f->height, n, points_xy, depths, radii, point_offsets, point_list,
+                       point_list_capacity, ranges, &D, nullptr);
   if (num_rendered_host) *num_rendered_host = D;
-  if (D > (1LL << 30))  // forward.py:765-767
-    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "Number of rendered points exceeds the maximum supported by Warp.");
-  if (D > GSB_MAX_RENDERED)
-    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "num_rendered == 2^30 is not supported by the radix sort (max 2^30-1)");
-  if (D > point_list_capacity)
-    return gsb_set_error(ctx, GSB_ERR_CAPACITY, "point_list capacity %lld < num_rendered %lld",
-                         (long long)point_list_capacity, (long long)D);
-
+  if (rc != GSB_OK) return rc;
   if (D == 0) {
     // forward.py:830: nothing is launched; every image-shaped output keeps its wp.zeros() state
     // (ranges were already written as all (0,0) by the counting pass)
@@ -213,26 +253,6 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
     GSB_CUDA(ctx, cudaMemsetAsync(final_T, 0, sizeof(float) * pixels, s));
     GSB_CUDA(ctx, cudaMemsetAsync(n_contrib, 0, sizeof(int32_t) * pixels, s));
     return GSB_OK;
-  }
-  if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
-    // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
-    rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, point_offsets, ranges, D,
-                               max_count, point_list);
-    if (rc != GSB_OK) return rc;
-  } else {
-    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
-    // forward.py:776-788
-    rc = gsb_duplicate_with_keys(ctx, s_, f->width, f->height, n, points_xy, depths, point_offsets, radii, D, ctx->keys_a,
-                                 ctx->vals_a);
-    if (rc != GSB_OK) return rc;
-    // forward.py:791-824; the final pass writes the sorted values straight into point_list
-    bool in_b = false;
-    rc = gsb_radix_sort_pingpong(ctx, s, ctx->keys_a, ctx->vals_a, ctx->keys_b, ctx->vals_b, point_list, D, 0,
-                                 key_bits_for(num_tiles), &in_b);
-    if (rc != GSB_OK) return rc;
-    const int64_t* sorted_keys = in_b ? ctx->keys_b : ctx->keys_a;
-    // forward.py:832-840
-    if ((rc = gsb_tile_ranges(ctx, s_, D, sorted_keys, num_tiles, ranges)) != GSB_OK) return rc;
   }
   // forward.py:844-863 (+ the no-op track_pixel_stats of 867-879)
   return gsb_blend_forward(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,

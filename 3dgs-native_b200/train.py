@@ -33,6 +33,26 @@ SHAPE = {"positions": lambda n: (n, 3), "scales": lambda n: (n, 3), "rotations":
          "opacities": lambda n: (n,), "shs": lambda n: (n * 16, 3)}
 
 
+def shard_views(batch, rank: int, world_size: int):
+    """Contiguous split of a step's global view batch over the ranks: rank r takes
+    batch[r*B/G : (r+1)*B/G].  The batch must be a multiple of the world size."""
+    B = len(batch)
+    per = B // world_size
+    if per * world_size != B or per < 1:
+        raise ValueError(f"batch of {B} views cannot be split evenly over {world_size} ranks")
+    return list(batch[rank * per:(rank + 1) * per])
+
+
+def flat_layout(n: int):
+    """Offsets (in floats) of the five tensors inside a FlatGaussians buffer and its total length:
+    every segment starts on a 16-byte boundary."""
+    offs, total = {}, 0
+    for k in KEYS:
+        offs[k] = total
+        total += (n * WIDTH[k] + 3) // 4 * 4
+    return offs, max(total, 4)
+
+
 class FlatGaussians:
     """One contiguous fp32 buffer holding the five per-Gaussian tensors back to back (each segment
     starts on a 16-byte boundary), with views of the reference's shapes.  The gradient instance of
@@ -40,11 +60,8 @@ class FlatGaussians:
 
     def __init__(self, n: int, device, fill: float | None = 0.0):
         self.n = n
-        offs, total = {}, 0
-        for k in KEYS:
-            offs[k] = total
-            total += (n * WIDTH[k] + 3) // 4 * 4
-        self.flat = (torch.zeros if fill == 0.0 else torch.empty)(max(total, 4), dtype=torch.float32, device=device)
+        offs, total = flat_layout(n)
+        self.flat = (torch.zeros if fill == 0.0 else torch.empty)(total, dtype=torch.float32, device=device)
         self.views = {k: self.flat[offs[k]: offs[k] + n * WIDTH[k]].view(SHAPE[k](n)) for k in KEYS}
 
     def __getitem__(self, k):
@@ -233,10 +250,7 @@ class Trainer:
         contiguous slice [rank*B/G, (rank+1)*B/G).  With one view and one rank this is exactly one
         iteration of the reference loop.  Returns the device tensor holding this rank's last
         sum|render - target| (divide by 3HW for the reference's loss)."""
-        B = len(cam_indices)
-        per = B // self.world_size
-        assert per * self.world_size == B and per >= 1, "batch must be a multiple of the world size"
-        mine = range(self.rank * per, (self.rank + 1) * per)
+        mine = shard_views(list(range(len(cam_indices))), self.rank, self.world_size)
         fb = None
         for j, b in enumerate(mine):
             ci = cam_indices[b]

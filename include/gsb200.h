@@ -106,6 +106,18 @@ int gsb_sort_pairs64(gsb_ctx* ctx, gsb_stream s, int64_t* keys, int32_t* values,
 int gsb_tile_ranges(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered, const int64_t* sorted_keys,
                     int32_t num_tiles, int32_t* ranges);
 
+/* replaces forward.py:776-840 as a whole (wp_duplicate_with_keys + radix_sort_pairs +
+ * wp_identify_tile_ranges): counting sort by tile + per-tile shared-memory sort on (depth, id).
+ * Produces the same point_list / ranges as the three stages above.  Needs point_offsets from
+ * gsb_scan_tiles.  Synchronises once; *num_rendered_host receives D.  Returns GSB_ERR_CAPACITY
+ * if D > point_list_capacity (ranges valid, point_list untouched).  *used_tile_path_host (may be
+ * NULL) tells whether the per-tile path ran (1) or a tile was longer than 16384 entries and the
+ * global radix sort was used instead (0). */
+int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s, int32_t width, int32_t height, int32_t n, const float* points_xy,
+                    const float* depths, const int32_t* radii, const int32_t* point_offsets, int32_t* point_list,
+                    int64_t point_list_capacity, int32_t* ranges, int64_t* num_rendered_host,
+                    int32_t* used_tile_path_host);
+
 /* replaces wp_render_gaussians (forward.py:384-515) and the no-op track_pixel_stats (589-627).
  * image float[H][W][3], inv_depth float[H][W], final_T float[H][W], n_contrib int32[H][W]. */
 int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, const int32_t* ranges,

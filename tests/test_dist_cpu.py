@@ -1,0 +1,104 @@
+"""CPU (gloo, world_size 2): the view-sharded data-parallel step -- contiguous view split, one
+all-reduce(SUM) of the flat 59*N gradient buffer, identical Adam on every rank -- equals the
+single-process step on the whole batch.  Per-view gradients come from the CPU oracle (this is a
+test of the host-side sharding logic, not of the kernels)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ("positions", "scales", "rotations", "opacities", "shs")
+GKEYS = {"positions": "dL_dmean3D", "scales": "dL_dscale", "rotations": "dL_drot", "opacities": "dL_dopacity",
+         "shs": "dL_dshs"}
+
+
+def _setup_paths():
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def _view_grads_flat(O, scene, train, params, cam, target):
+    n = params["positions"].shape[0]
+    img, _, buf = O.render_gaussians(**scene.render_kwargs(params, cam))
+    dpix = O.compute_image_gradients(img, target, lambda_dssim=0)
+    g = O.backward(**scene.backward_kwargs(params, cam, buf, dpix))
+    offs, total = train.flat_layout(n)
+    flat = np.zeros(total, np.float32)
+    for k in KEYS:
+        v = g[GKEYS[k]].reshape(-1)
+        flat[offs[k]:offs[k] + v.size] = v
+    return flat
+
+
+def _worker(rank, world, port, batch, out_dir):
+    _setup_paths()
+    import gsb200  # noqa: F401
+    from gsb200 import scene, train
+    from gsb200.utils.camera_utils import load_nerf_cameras
+    import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, w, h = 300, 48, 32
+    params, _, _ = scene.synthetic_scene(n, w, h, 0.05, 0.3, seed=9, with_target=False)
+    cams = load_nerf_cameras(w, h)
+    rng = np.random.default_rng(2)
+    targets = {ci: rng.uniform(0, 1, (h, w, 3)).astype(np.float32) for ci in sorted(set(batch))}
+    mine = train.shard_views(batch, rank, world)
+    flat = None
+    for ci in mine:                                   # sum over this rank's views
+        f = _view_grads_flat(O, scene, train, params, cams[ci], targets[ci])
+        flat = f if flat is None else flat + f
+    t = torch.from_numpy(flat)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)          # the ONE exchange step
+    np.save(os.path.join(out_dir, f"grads_rank{rank}.npy"), t.numpy())
+    np.save(os.path.join(out_dir, f"views_rank{rank}.npy"), np.array(mine))
+    dist.destroy_process_group()
+
+
+def test_view_sharded_step_equals_single_process(tmp_path):
+    _setup_paths()
+    import gsb200  # noqa: F401
+    from gsb200 import scene, train
+    from gsb200.utils.camera_utils import load_nerf_cameras
+    import oracle as O
+    O.build()
+    batch = [3, 17, 42, 8]
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, batch, str(tmp_path)), nprocs=world, join=True)
+    g0 = np.load(tmp_path / "grads_rank0.npy")
+    g1 = np.load(tmp_path / "grads_rank1.npy")
+    assert np.array_equal(g0, g1)                     # every rank holds the same reduced gradients
+    assert np.load(tmp_path / "views_rank0.npy").tolist() == [3, 17]
+    assert np.load(tmp_path / "views_rank1.npy").tolist() == [42, 8]
+    # single process: sum over the whole batch
+    n, w, h = 300, 48, 32
+    params, _, _ = scene.synthetic_scene(n, w, h, 0.05, 0.3, seed=9, with_target=False)
+    cams = load_nerf_cameras(w, h)
+    rng = np.random.default_rng(2)
+    targets = {ci: rng.uniform(0, 1, (h, w, 3)).astype(np.float32) for ci in sorted(set(batch))}
+    ref = None
+    for ci in batch:
+        f = _view_grads_flat(O, scene, train, params, cams[ci], targets[ci])
+        ref = f if ref is None else ref + f
+    assert np.allclose(g0, ref, rtol=1e-5, atol=1e-9)  # float summation order differs (2+2 vs 4)
+    assert np.linalg.norm(ref) > 0
+
+
+def test_shard_views_rejects_ragged_batches():
+    _setup_paths()
+    import gsb200  # noqa: F401
+    from gsb200 import train
+    assert train.shard_views([5, 6, 7, 8], 1, 2) == [7, 8]
+    assert train.shard_views([9], 0, 1) == [9]
+    with pytest.raises(ValueError):
+        train.shard_views([1, 2, 3], 0, 2)
+    offs, total = train.flat_layout(5)
+    assert offs["positions"] == 0 and all(o % 4 == 0 for o in offs.values()) and total >= 59 * 5

@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -319,7 +319,6 @@ def ours(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = T.ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
     value = K * world / (ms_total * 1e-3)
 
     # ---- pure forward+backward of the single-view headline (camera 0) ---------------------------
@@ -383,6 +382,8 @@ def ours(args):
         e2e = {"value": K * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(h * w * 3 * 4 + 2 * 64 + 24),
                "d2h_bytes_per_step": 8 + 8, "ms_per_step": dt / K * 1e3,
                "api": "forward.render_gaussians + loss.l1_loss_and_gradients + backward.backward + optimizer.adam_update"}
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled across all timed loops above
 
     # ---- per-stage table + roofline of the dominant kernel (rank 0) -----------------------------------
     stages, roofline = None, None

@@ -49,6 +49,9 @@ _SIGS = {
     "gsb_preprocess_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 15),
     "gsb_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 25),
     "gsb_adam_step": (C.c_int, [vp, vp, i32] + [vp] * 5 + [f32] * 8 + [i32] + [vp] * 15),
+    "gsb_flat_layout": (C.c_int, [i32, C.POINTER(i64), C.POINTER(i64)]),
+    "gsb_adam_step_peers": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64,
+                                      C.c_uint64, vp, vp] + [f32] * 8 + [i32]),
     "gsb_fill_f32": (C.c_int, [vp, vp, vp, i64, f32]),
     "gsb_accumulate_f32": (C.c_int, [vp, vp, vp, vp, i64]),
     "gsb_init_gaussian_params": (C.c_int, [vp, vp, i32, f32] + [vp] * 5),

@@ -58,10 +58,19 @@ class FlatGaussians:
     starts on a 16-byte boundary), with views of the reference's shapes.  The gradient instance of
     this class is what gets all-reduced: one message of 59*N floats."""
 
-    def __init__(self, n: int, device, fill: float | None = 0.0):
+    def __init__(self, n: int, device, fill: float | None = 0.0, symmetric_group=None):
         self.n = n
         offs, total = flat_layout(n)
-        self.flat = (torch.zeros if fill == 0.0 else torch.empty)(total, dtype=torch.float32, device=device)
+        self.symm = None
+        if symmetric_group is not None:
+            # symmetric memory: every rank can address every other rank's copy (NVLink peer mapping,
+            # plus an NVSwitch multicast address when the fabric supports it)
+            import torch.distributed._symmetric_memory as symm_mem
+            self.flat = symm_mem.empty(total, dtype=torch.float32, device=device)
+            self.flat.zero_()
+            self.symm = symm_mem.rendezvous(self.flat, symmetric_group)
+        else:
+            self.flat = (torch.zeros if fill == 0.0 else torch.empty)(total, dtype=torch.float32, device=device)
         self.views = {k: self.flat[offs[k]: offs[k] + n * WIDTH[k]].view(SHAPE[k](n)) for k in KEYS}
 
     def __getitem__(self, k):
@@ -112,13 +121,19 @@ class FrameBuffers:
 
 class Trainer:
     def __init__(self, cameras, targets=None, num_points=None, params=None, config=None, device=None,
-                 rank=0, world_size=1, process_group=None):
+                 rank=0, world_size=1, process_group=None, exchange="auto"):
+        """``exchange`` selects how the gradient sum and the Adam step are done when world_size > 1:
+        "nccl" = all_reduce + replicated Adam; "peers" / "multimem" = the fused kernel of
+        gsb_adam_step_peers over symmetric memory (NVLink loads / NVSwitch in-fabric reduction);
+        "auto" = peers when symmetric memory is available (measured fastest at 2 and 8 B200s:
+        4470 vs 4349 multimem vs 3986 nccl views/s at 8 GPUs), else nccl."""
         self.config = GaussianParams.get_config_dict()
         if config:
             self.config.update(config)
         self.ctx = _lib.context(device)
         self.device = torch.device("cuda", self.ctx.device_index)
         self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.exchange = self._pick_exchange(exchange)
         self.cameras = cameras
         bg = self.config["background_color"]
         self.frames = [_lib.make_frame(c["world_to_camera"], c["full_proj_matrix"], c["camera_center"], c["tan_fovx"],
@@ -131,10 +146,10 @@ class Trainer:
             n = int(np.asarray(params["positions"].shape)[0]) if not isinstance(params["positions"], torch.Tensor) \
                 else params["positions"].shape[0]
             self.num_points = n
-            self.params = FlatGaussians(n, self.device).load(params)
+            self.params = self._new_flat(n).load(params)
         else:
             self.num_points = n = int(num_points or self.config["num_points"])
-            self.params = FlatGaussians(n, self.device)
+            self.params = self._new_flat(n)
             optimizer.init_gaussian_params(self.params["positions"], self.params["scales"], self.params["rotations"],
                                            self.params["opacities"], self.params["shs"], n, self.config["initial_scale"])
         self._alloc_state()
@@ -147,10 +162,36 @@ class Trainer:
         self.losses = []
 
     # ---- state -------------------------------------------------------------------------------
+    def _pick_exchange(self, want):
+        if self.world_size <= 1:
+            return "none"
+        if want == "nccl":
+            return "nccl"
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            probe = symm_mem.empty(4, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(probe, group)
+            has_mc = int(getattr(hdl, "multicast_ptr", 0) or 0) != 0
+            self._symm_group = group
+        except Exception as e:  # no peer access / symmetric memory unavailable
+            if want in ("peers", "multimem"):
+                raise RuntimeError(f"exchange={want!r} needs symmetric memory: {e}") from e
+            return "nccl"
+        if want == "multimem" and not has_mc:
+            raise RuntimeError("exchange='multimem' requested but the fabric offers no multicast mapping")
+        return "multimem" if want == "multimem" else "peers"
+
+    def _new_flat(self, n, symmetric=True):
+        if symmetric and self.exchange in ("peers", "multimem"):
+            return FlatGaussians(n, self.device, symmetric_group=self._symm_group)
+        return FlatGaussians(n, self.device)
+
     def _alloc_state(self):
         n = self.num_points
-        self.grads = FlatGaussians(n, self.device)      # train.py:160-164 (zeros)
-        self.adam_m = FlatGaussians(n, self.device)
+        self.grads = self._new_flat(n)                  # train.py:160-164 (zeros)
+        self.adam_m = FlatGaussians(n, self.device)     # only this rank's shard is used in the fused modes
         self.adam_v = FlatGaussians(n, self.device)
         self.grads_tmp = None
         self.fb = None
@@ -245,6 +286,31 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
 
+    def exchange_and_step(self, iteration):
+        """Gradient sum over the ranks + Adam.  nccl: all_reduce then the replicated fused Adam.
+        peers / multimem: ONE kernel between two cross-rank barriers -- each rank reduces its shard
+        of the gradients straight out of its peers' buffers, updates that shard, and writes the new
+        parameters into every rank's buffer (gsb_adam_step_peers)."""
+        if self.exchange in ("none", "nccl"):
+            self.all_reduce_gradients()
+            self.optimizer_step(iteration)
+            return
+        G, P = self.grads.symm, self.params.symm
+        lr = self.learning_rates(iteration)
+        W = self.world_size
+        gp = (C.c_uint64 * W)(*[int(x) for x in G.buffer_ptrs])
+        pp = (C.c_uint64 * W)(*[int(x) for x in P.buffer_ptrs])
+        use_mc = self.exchange == "multimem"
+        g_mc = int(G.multicast_ptr) if use_mc else 0
+        p_mc = int(P.multicast_ptr) if use_mc else 0
+        G.barrier(channel=0)        # every rank's backward has finished writing its gradients
+        self.ctx.check(_lib.lib().gsb_adam_step_peers(
+            self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, g_mc, p_mc,
+            _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
+            lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
+            self.config["adam_epsilon"], iteration))
+        P.barrier(channel=1)        # every rank's parameter shard has landed everywhere
+
     def train_step(self, iteration: int, cam_indices, targets=None, densify=True):
         """One step on a batch of views.  ``cam_indices`` is the GLOBAL batch; this rank takes the
         contiguous slice [rank*B/G, (rank+1)*B/G).  With one view and one rank this is exactly one
@@ -256,15 +322,14 @@ class Trainer:
             ci = cam_indices[b]
             tgt = targets[b] if targets is not None else self.targets[ci]
             fb = self.accumulate_view(ci, tgt, first=(j == 0))
-        self.all_reduce_gradients()
-        self.optimizer_step(iteration)
+        self.exchange_and_step(iteration)
         if densify:
             self.densification_and_pruning(iteration)
         return fb.loss_sum
 
     # ---- densify / prune, train.py:351-713 ------------------------------------------------------
     def _alloc_like(self, n):
-        return FlatGaussians(n, self.device)          # wp.zeros outputs of train.py:441-447 etc.
+        return self._new_flat(n)                       # wp.zeros outputs of train.py:441-447 etc.
 
     def _replace(self, new: FlatGaussians):
         self.params, self.num_points = new, new.n

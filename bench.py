@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--ppt-fwd", type=int, default=0)
     ap.add_argument("--ppt-bwd", type=int, default=0)
     ap.add_argument("--cull", type=int, default=1)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
@@ -268,6 +269,9 @@ def ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the one JSON line: some images export NCCL_DEBUG=VERSION, which prints there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -279,7 +283,7 @@ def ours(args):
     lr_scale = 1e-4
     lrs = {k: (v * lr_scale if k != "final_lr_factor" else v)
            for k, v in train.GaussianParams.lr_scheduler_config.items()}
-    T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world,
+    T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=args.exchange,
                       config={"num_iterations": 7000, "lr_scheduler_config": lrs})
     T.ctx.set_option("blend_cull", args.cull)
     if args.ppt_fwd:
@@ -419,7 +423,11 @@ def ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {n} synthetic Gaussians (SH degree 3), {w}x{h}, Lego train poses; "
                                    "one train view per rank per step = forward + L1 loss/gradient + backward"
-                                   + (" + NCCL all-reduce of 59*N gradient floats" if world > 1 else "") + " + Adam",
+                                   + ({"nccl": " + NCCL all-reduce of 59*N gradient floats + replicated Adam",
+                                       "peers": " + fused NVLink peer-load gradient reduction/Adam/parameter broadcast kernel",
+                                       "multimem": " + fused NVSwitch multimem gradient reduction/Adam/parameter broadcast kernel",
+                                       "none": " + Adam"}[T.exchange]),
+                       "exchange": T.exchange,
                        "views_per_step": world, "num_rendered_view0": int(num_rendered), "densify": "off (fixed N)",
                        "learning_rates": "reference values x 1e-4 (keeps the synthetic scene at the named shape)",
                        "l2": "per-step working set ~0.5 GB (params, grads, Adam state, binning buffers) > 126 MB L2; "

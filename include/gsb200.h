@@ -178,6 +178,25 @@ int gsb_adam_step(gsb_ctx* ctx, gsb_stream s, int32_t n, const float* g_pos, con
                   float* m_scale, float* m_rot, float* m_opac, float* m_sh, float* v_pos, float* v_scale,
                   float* v_rot, float* v_opac, float* v_sh);
 
+/* Layout of the "flat" per-role buffer used by the data-parallel trainer: positions | scales |
+ * rotations | opacities | SH back to back, every segment starting on a 16-byte boundary.
+ * offsets5 receives the five offsets in floats, *total the length in floats. */
+int gsb_flat_layout(int32_t n, int64_t* offsets5, int64_t* total);
+
+/* Fused gradient exchange + Adam for view-sharded data parallelism (no reference counterpart:
+ * the reference trains on one device).  grad_ptrs_host / param_ptrs_host are HOST arrays of `world`
+ * device addresses: every rank's flat gradient / parameter buffer as mapped into THIS process
+ * (symmetric memory / CUDA IPC); grad_multicast / param_multicast are NVLS multicast addresses of
+ * the same buffers or 0.  The kernel sums the gradients of this rank's shard of Gaussians over all
+ * ranks (multimem.ld_reduce through the NVSwitch, or one NVLink load per peer), applies
+ * adam_update (optimizer.py:6-139) to the shard of m_flat / v_flat, and stores the new parameters
+ * into every rank's buffer.  The caller orders it between two cross-rank barriers. */
+int gsb_adam_step_peers(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, int32_t rank,
+                        const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host, uint64_t grad_multicast,
+                        uint64_t param_multicast, float* m_flat, float* v_flat, float lr_pos, float lr_scale,
+                        float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
+                        int32_t iteration);
+
 /* replaces zero_gradients (train.py:94-115) -- and any other "fill float" need */
 int gsb_fill_f32(gsb_ctx* ctx, gsb_stream s, float* dst, int64_t count, float value);
 /* out += in (view-batch gradient accumulation; no reference counterpart: batch size is 1 there) */

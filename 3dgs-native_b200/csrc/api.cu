@@ -17,8 +17,6 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                           const int32_t* ranges, int64_t num_rendered, int max_count, int32_t* point_list);
 int gsb_tile_binning_max();
 int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
-extern int g_blend_fwd_ppt;
-extern int g_blend_bwd_ppt;
 int g_blend_cull = 1;
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
@@ -134,18 +132,9 @@ GSB_API int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered) {
   return gsb_reserve_binning(ctx, (cudaStream_t)s, num_rendered);
 }
 
-// tuning knobs (not part of the reference surface): "blend_fwd_ppt", "blend_bwd_ppt" in {1,2,4,8}
+// A/B knobs (not part of the reference surface; results never depend on them)
 GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
   if (!name) return GSB_ERR_INVALID;
-  const bool ok = (value == 1 || value == 2 || value == 4 || value == 8);
-  if (!strcmp(name, "blend_fwd_ppt") && ok) {
-    g_blend_fwd_ppt = value;
-    return GSB_OK;
-  }
-  if (!strcmp(name, "blend_bwd_ppt") && ok) {
-    g_blend_bwd_ppt = value;
-    return GSB_OK;
-  }
   if (!strcmp(name, "binning") && (value == 0 || value == 1)) {
     g_binning = value;
     return GSB_OK;

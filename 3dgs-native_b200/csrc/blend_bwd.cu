@@ -50,57 +50,44 @@ __device__ __forceinline__ void warp_reduce9_red(float v[9], int lane, int gid, 
   }
 }
 
-template <int PPT>
-__global__ void __launch_bounds__(256 / PPT, PPT == 1 ? 4 : 1)
+__global__ void __launch_bounds__(256, 4)
 blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
                       const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                       const float* __restrict__ rgb, const float* __restrict__ final_T,
                       const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
                       float* __restrict__ dL_dcolor) {
-  constexpr int NT = 256 / PPT;
-  constexpr int NW = NT / 32;
-  __shared__ float4 s_a[NT];  // x, y, conic.a, conic.b
-  __shared__ float4 s_b[NT];  // conic.c, opacity, power threshold, -
-  __shared__ float4 s_c[NT];  // r, g, b, gid (bits)
-  __shared__ int2 s_meta[NT]; // position in the tile's list, row mask
+  constexpr int NT = 256, NW = 8;
+  __shared__ float4 s_a[NT];   // x, y, conic.a, conic.b
+  __shared__ float4 s_b[NT];   // conic.c, opacity, power threshold, -
+  __shared__ float4 s_c[NT];   // r, g, b, gid (bits)
+  __shared__ int2 s_meta[NT];  // position in the tile's list, block mask
   __shared__ int s_max[NW];
   __shared__ int s_wcnt[NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int tile_id = tile_y * P.grid_x + tile_x;
-  const int px = tile_x * kTile + (lane & 15);
-  const int row0 = tile_y * kTile + warp * (2 * PPT) + (lane >> 4);
-  const float pxf = (float)px;
+  const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
+  const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+  const float pxf = (float)px, pyf = (float)py;
   const int2 range = ranges[tile_id];
-  const unsigned my_rows = ((1u << (2 * PPT)) - 1u) << (warp * 2 * PPT);
+  const unsigned my_mask = gs_warp_mask(warp);
   const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
 
-  float pyf[PPT], T[PPT], T_final[PPT], acc0[PPT], acc1[PPT], acc2[PPT], last_alpha[PPT], lc0[PPT], lc1[PPT], lc2[PPT];
-  float dp0[PPT], dp1[PPT], dp2[PPT], bgdot[PPT];
-  int kept[PPT];
-  int my_max = 0;
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const int py = row0 + 2 * k;
-    pyf[k] = (float)py;
-    const bool inside = (px < P.W && py < P.H);
-    const size_t pix = inside ? ((size_t)py * P.W + px) : 0;
-    T_final[k] = inside ? final_T[pix] : 0.0f;
-    T[k] = T_final[k];
-    // backward.py:619 last_kept = min(range_end, range_start + n_contrib), relative to range_start
-    kept[k] = inside ? min(range.y - range.x, n_contrib[pix]) : 0;
-    my_max = max(my_max, kept[k]);
-    dp0[k] = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
-    dp1[k] = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
-    dp2[k] = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
-    bgdot[k] = gs_dot3(P.bg0, P.bg1, P.bg2, dp0[k], dp1[k], dp2[k]);  // backward.py:679
-    acc0[k] = acc1[k] = acc2[k] = 0.0f;
-    last_alpha[k] = 0.0f;
-    lc0[k] = lc1[k] = lc2[k] = 0.0f;
-  }
-  my_max = __reduce_max_sync(0xffffffffu, my_max);
+  const bool inside = (px < P.W && py < P.H);
+  const size_t pix = inside ? ((size_t)py * P.W + px) : 0;
+  const float T_final = inside ? final_T[pix] : 0.0f;
+  float T = T_final;
+  // backward.py:619 last_kept = min(range_end, range_start + n_contrib), relative to range_start
+  const int kept = inside ? min(range.y - range.x, n_contrib[pix]) : 0;
+  const float dp0 = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
+  const float dp1 = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
+  const float dp2 = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
+  const float bgdot = gs_dot3(P.bg0, P.bg1, P.bg2, dp0, dp1, dp2);  // backward.py:679
+  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, last_alpha = 0.0f, lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;
+
+  const int my_max = __reduce_max_sync(0xffffffffu, kept);
   if (lane == 0) s_max[warp] = my_max;
   __syncthreads();
   int tile_max = 0;
@@ -114,100 +101,85 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
     const int n_in = min(NT, hi);
     __syncthreads();
     float4 ea, eb, ec;
-    unsigned rowmask = 0u;
+    unsigned bmask = 0u;
     if (tid < n_in) {
       const int gid = point_list[range.x + hi - 1 - tid];
       const float2 p = xy[gid];
       const float4 co = conic_opacity[gid];
       const float thr = gs_power_threshold(co.w);
-      rowmask = P.cull ? gs_row_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffu;
+      bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
       ea = make_float4(p.x, p.y, co.x, co.y);
       eb = make_float4(co.z, co.w, thr, 0.0f);
       ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
     }
     int cnt;
-    const int slot = compact_slot<NW>(rowmask != 0u, lane, warp, s_wcnt, cnt);
-    if (rowmask != 0u) {
+    const int slot = compact_slot<NW>(bmask != 0u, lane, warp, s_wcnt, cnt);
+    if (bmask != 0u) {
       s_a[slot] = ea;
       s_b[slot] = eb;
       s_c[slot] = ec;
-      s_meta[slot] = make_int2(hi - 1 - tid, (int)rowmask);
+      s_meta[slot] = make_int2(hi - 1 - tid, (int)bmask);
     }
     __syncthreads();
     // a warp whose pixels all stopped before this batch has nothing to do in it
     if (my_max <= hi - n_in) continue;
     for (int j = 0; j < cnt; ++j) {
       const int2 meta = s_meta[j];
-      const int pos = meta.x;      // position in the tile's list; pixel k replays it iff pos < kept[k]
+      const int pos = meta.x;      // position in the tile's list; the pixel replays it iff pos < kept
       if (pos >= my_max) continue; // warp-uniform
-      if (!((unsigned)meta.y & my_rows)) continue;  // warp-uniform
+      if (!((unsigned)meta.y & my_mask)) continue;  // warp-uniform
       const float4 a = s_a[j];
       const float4 b = s_b[j];
-      const float4 c = s_c[j];
       const float dx = a.x - pxf;
+      const float dy = a.y - pyf;
       float g[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) g[q] = 0.0f;
       bool any = false;
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        if (pos >= kept[k]) continue;
-        const float dy = a.y - pyf[k];
-        const float power = gs_power(a.z, a.w, b.x, dx, dy);
-        if (power > 0.0f) continue;  // backward.py:647
-        if (power < b.z) continue;   // provably alpha < 1/255
+      const float power = gs_power(a.z, a.w, b.x, dx, dy);
+      // backward.py:647 (power > 0), the conservative exponent threshold, and the replay limit
+      if (pos < kept && !(power > 0.0f) && !(power < b.z)) {
         const float G = gs_expf(power);
         const float alpha = f_min(0.99f, b.y * G);
-        if (alpha < (1.0f / 255.0f)) continue;  // backward.py:655
-        const float inv_1ma = 1.0f / (1.0f - alpha);   // backward.py:658,680 divide twice by (1 - alpha)
-        T[k] = T[k] * inv_1ma;
-        const float dchannel_dcolor = alpha * T[k];
-        acc0[k] = last_alpha[k] * lc0[k] + (1.0f - last_alpha[k]) * acc0[k];
-        acc1[k] = last_alpha[k] * lc1[k] + (1.0f - last_alpha[k]) * acc1[k];
-        acc2[k] = last_alpha[k] * lc2[k] + (1.0f - last_alpha[k]) * acc2[k];
-        lc0[k] = c.x;
-        lc1[k] = c.y;
-        lc2[k] = c.z;
-        float dL_dalpha = gs_dot3(c.x - acc0[k], c.y - acc1[k], c.z - acc2[k], dp0[k], dp1[k], dp2[k]);
-        g[0] += dchannel_dcolor * dp0[k];
-        g[1] += dchannel_dcolor * dp1[k];
-        g[2] += dchannel_dcolor * dp2[k];
-        dL_dalpha *= T[k];
-        last_alpha[k] = alpha;
-        dL_dalpha += (-T_final[k] * inv_1ma) * bgdot[k];
-        const float dL_dG = b.y * dL_dalpha;
-        const float gdx = G * dx;
-        const float gdy = G * dy;
-        const float dG_ddelx = -gdx * a.z - gdy * a.w;
-        const float dG_ddely = -gdy * b.x - gdx * a.w;
-        g[3] += dL_dG * dG_ddelx * ddelx_dx;
-        g[4] += dL_dG * dG_ddely * ddely_dy;
-        g[5] += -0.5f * gdx * dx * dL_dG;
-        g[6] += -0.5f * gdx * dy * dL_dG;
-        g[7] += -0.5f * gdy * dy * dL_dG;
-        g[8] += G * dL_dalpha;
-        any = true;
+        if (!(alpha < (1.0f / 255.0f))) {  // backward.py:655
+          const float4 c = s_c[j];
+          const float inv_1ma = 1.0f / (1.0f - alpha);   // backward.py:658,680 divide twice by (1 - alpha)
+          T = T * inv_1ma;
+          const float dchannel_dcolor = alpha * T;
+          acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
+          acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
+          acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
+          lc0 = c.x;
+          lc1 = c.y;
+          lc2 = c.z;
+          float dL_dalpha = gs_dot3(c.x - acc0, c.y - acc1, c.z - acc2, dp0, dp1, dp2);
+          g[0] = dchannel_dcolor * dp0;
+          g[1] = dchannel_dcolor * dp1;
+          g[2] = dchannel_dcolor * dp2;
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final * inv_1ma) * bgdot;
+          const float dL_dG = b.y * dL_dalpha;
+          const float gdx = G * dx;
+          const float gdy = G * dy;
+          const float dG_ddelx = -gdx * a.z - gdy * a.w;
+          const float dG_ddely = -gdy * b.x - gdx * a.w;
+          g[3] = dL_dG * dG_ddelx * ddelx_dx;
+          g[4] = dL_dG * dG_ddely * ddely_dy;
+          g[5] = -0.5f * gdx * dx * dL_dG;
+          g[6] = -0.5f * gdx * dy * dL_dG;
+          g[7] = -0.5f * gdy * dy * dL_dG;
+          g[8] = G * dL_dalpha;
+          any = true;
+        }
       }
       if (__any_sync(0xffffffffu, any))
-        warp_reduce9_red(g, lane, __float_as_int(c.w), dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+        warp_reduce9_red(g, lane, __float_as_int(s_c[j].w), dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
     }
   }
 }
 
-template <int PPT>
-int launch_bwd(gsb_ctx* ctx, cudaStream_t s, const BlendParams& P, dim3 grid, const int32_t* ranges,
-               const int32_t* point_list, const float* xy, const float* conic_opacity, const float* rgb,
-               const float* final_T, const int32_t* n_contrib, const float* dL_dpixels, float* dL_dmean2D,
-               float* dL_dconic, float* dL_dopacity, float* dL_dcolor) {
-  GSB_LAUNCH(ctx, blend_backward_kernel<PPT>, grid, 256 / PPT, 0, s, P, reinterpret_cast<const int2*>(ranges),
-             point_list, reinterpret_cast<const float2*>(xy), reinterpret_cast<const float4*>(conic_opacity), rgb,
-             final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-  return GSB_OK;
-}
-
 }  // namespace
-
-int g_blend_bwd_ppt = 1;
 
 GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const int32_t* ranges,
                                const int32_t* point_list, const float* points_xy, const float* conic_opacity,
@@ -225,10 +197,8 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
   GSB_CUDA(ctx, cudaMemsetAsync(dL_dcolor, 0, sizeof(float) * 3 * (size_t)n, s));
   BlendParams P = make_blend_params(f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  switch (g_blend_bwd_ppt) {
-    case 2: return launch_bwd<2>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-    case 4: return launch_bwd<4>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-    case 8: return launch_bwd<8>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-    default: return launch_bwd<1>(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-  }
+  GSB_LAUNCH(ctx, blend_backward_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
+             reinterpret_cast<const float2*>(points_xy), reinterpret_cast<const float4*>(conic_opacity), rgb, final_T,
+             n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+  return GSB_OK;
 }

@@ -42,8 +42,6 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
-    ap.add_argument("--ppt-fwd", type=int, default=0)
-    ap.add_argument("--ppt-bwd", type=int, default=0)
     ap.add_argument("--cull", type=int, default=1)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -286,10 +284,6 @@ def ours(args):
     T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=args.exchange,
                       config={"num_iterations": 7000, "lr_scheduler_config": lrs})
     T.ctx.set_option("blend_cull", args.cull)
-    if args.ppt_fwd:
-        T.ctx.set_option("blend_fwd_ppt", args.ppt_fwd)
-    if args.ppt_bwd:
-        T.ctx.set_option("blend_bwd_ppt", args.ppt_bwd)
 
     def batch(it):   # one view per rank per step, cycling through the poses
         return [(it * world + r) % N_CAMERAS for r in range(world)]
@@ -431,7 +425,7 @@ def ours(args):
                        "views_per_step": world, "num_rendered_view0": int(num_rendered), "densify": "off (fixed N)",
                        "learning_rates": "reference values x 1e-4 (keeps the synthetic scene at the named shape)",
                        "l2": "per-step working set ~0.5 GB (params, grads, Adam state, binning buffers) > 126 MB L2; "
-                             "no explicit flush", "blend_ppt": [args.ppt_fwd or 1, args.ppt_bwd or 1],
+                             "no explicit flush",
                        "host_cores": os.cpu_count()},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "fwd_bwd_frames_per_s": fwd_bwd_fps, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,

@@ -69,8 +69,7 @@ int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered);
 /* number of kernel launches issued through this context so far (bench.py gpu_launches) */
 int64_t gsb_launch_count(gsb_ctx* ctx);
 /* tuning / A-B knobs outside the reference surface (process-wide; results never depend on them):
- *   "blend_fwd_ppt" / "blend_bwd_ppt" = pixels per thread of the tile kernels: 1, 2, 4 or 8
- *   "blend_cull" = 1 (default) / 0: per-row culling masks in the tile kernels
+ *   "blend_cull" = 1 (default) / 0: per-block culling masks in the tile kernels
  *   "binning"    = 0 (default): gsb_forward bins by tile with a counting sort and sorts every tile's
  *                  segment in shared memory; 1: duplicate-with-keys + global 64-bit radix sort */
 int gsb_set_option(gsb_ctx* ctx, const char* name, int value);

@@ -99,12 +99,13 @@ def test_example_scene_config1(gs, oracle):
     assert got[2]["point_list"].numel() == 11779
 
 
-@pytest.mark.parametrize("n,w,h,smin,smax,ppt", [(3000, 100, 70, 0.01, 0.08, 1), (20000, 320, 240, 0.005, 0.05, 2),
-                                                 (20000, 333, 251, 0.005, 0.05, 4), (8000, 256, 256, 0.01, 0.1, 8)])
-def test_synthetic_forward_backward_vs_oracle(gs, oracle, n, w, h, smin, smax, ppt):
+@pytest.mark.parametrize("n,w,h,smin,smax,cull", [(3000, 100, 70, 0.01, 0.08, 1), (20000, 320, 240, 0.005, 0.05, 1),
+                                                  (20000, 333, 251, 0.005, 0.05, 0), (8000, 256, 256, 0.01, 0.1, 1),
+                                                  (2000, 40, 24, 0.3, 2.0, 1)])
+def test_synthetic_forward_backward_vs_oracle(gs, oracle, n, w, h, smin, smax, cull):
+    """cull = 0 switches the per-block culling masks of the tile kernels off: same results."""
     from gsb200 import _lib
-    _lib.context().set_option("blend_fwd_ppt", ppt)
-    _lib.context().set_option("blend_bwd_ppt", ppt)
+    _lib.context().set_option("blend_cull", cull)
     try:
         params, cam, target = gs.scene.synthetic_scene(n, w, h, smin, smax, seed=n + w)
         kw = gs.scene.render_kwargs(params, cam)
@@ -119,8 +120,7 @@ def test_synthetic_forward_backward_vs_oracle(gs, oracle, n, w, h, smin, smax, p
         check_grads(grads, ograds)
     finally:
         oracle.set_threads(1)
-        _lib.context().set_option("blend_fwd_ppt", 1)
-        _lib.context().set_option("blend_bwd_ppt", 1)
+        _lib.context().set_option("blend_cull", 1)
 
 
 def test_nothing_visible_gives_zero_image(gs, oracle):

@@ -42,6 +42,7 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
   __shared__ float4 s_c[NT];   // r, g, b, -
   __shared__ int2 s_meta[NT];  // 1-based position in the tile's list, block mask
   __shared__ int s_wcnt[NW];
+  __shared__ unsigned char s_widx[NW][NT];  // per warp: the staged entries that touch its block
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -83,10 +84,10 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
     }
     __syncthreads();
     if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are all finished
-    for (int j = 0; j < cnt; ++j) {
-      const int2 meta = s_meta[j];
-      if (!((unsigned)meta.y & my_mask)) continue;  // warp-uniform: this Gaussian cannot touch our block
+    const int wn = warp_compact_hits(s_meta, cnt, my_mask, 0x7fffffff, lane, s_widx[warp]);
+    for (int q = 0; q < wn; ++q) {
       if (done) continue;
+      const int j = s_widx[warp][q];
       const float4 a = s_a[j];
       const float4 b = s_b[j];
       const float dx = a.x - pxf;
@@ -107,7 +108,7 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
       C2 += c.z * alpha * T;
       Dp += b.w * alpha * T;
       T = test_T;
-      last = meta.x;
+      last = s_meta[j].x;
     }
   }
 

@@ -64,6 +64,7 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
   __shared__ int2 s_meta[NT];  // position in the tile's list, block mask
   __shared__ int s_max[NW];
   __shared__ int s_wcnt[NW];
+  __shared__ unsigned char s_widx[NW][NT];  // per warp: the staged entries it has to replay
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -123,11 +124,11 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
     __syncthreads();
     // a warp whose pixels all stopped before this batch has nothing to do in it
     if (my_max <= hi - n_in) continue;
-    for (int j = 0; j < cnt; ++j) {
-      const int2 meta = s_meta[j];
-      const int pos = meta.x;      // position in the tile's list; the pixel replays it iff pos < kept
-      if (pos >= my_max) continue; // warp-uniform
-      if (!((unsigned)meta.y & my_mask)) continue;  // warp-uniform
+    // entries that touch this warp's block and lie inside its replay range (position < my_max)
+    const int wn = warp_compact_hits(s_meta, cnt, my_mask, my_max, lane, s_widx[warp]);
+    for (int q = 0; q < wn; ++q) {
+      const int j = s_widx[warp][q];
+      const int pos = s_meta[j].x;  // position in the tile's list; the pixel replays it iff pos < kept
       const float4 a = s_a[j];
       const float4 b = s_b[j];
       const float dx = a.x - pxf;

@@ -74,6 +74,28 @@ __device__ __forceinline__ int compact_slot(bool keep, int lane, int warp, int* 
   return base + __popc(bal & ((1u << lane) - 1u));
 }
 
+// Per-warp compaction of the staged batch: the indices (0..cnt-1, in order) of the entries whose
+// block mask touches this warp's block -- and, for the backward, that lie inside the warp's replay
+// range (position < pos_limit) -- are written to widx[0..n).  One ballot per 32 entries; the main
+// loop then never sees an entry it would skip.
+__device__ __forceinline__ int warp_compact_hits(const int2* s_meta, int cnt, unsigned my_mask, int pos_limit, int lane,
+                                                 unsigned char* widx) {
+  int n = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int e = base + lane;
+    bool hit = false;
+    if (e < cnt) {
+      const int2 m = s_meta[e];
+      hit = (((unsigned)m.y & my_mask) != 0u) && (m.x < pos_limit);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) widx[n + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)e;
+    n += __popc(bal);
+  }
+  __syncwarp();
+  return n;
+}
+
 inline BlendParams make_blend_params(const gsb_frame* f) {
   BlendParams P;
   P.W = f->width;

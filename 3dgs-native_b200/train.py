@@ -406,6 +406,34 @@ class Trainer:
             log["opacity_reset"] = True
         return log
 
+    # ---- checkpoints (train.py:796-849 saves the PLY only; here the run can also be resumed) ------
+    def save_checkpoint(self, directory, iteration):
+        """point_cloud/iteration_N/point_cloud.ply in the reference's layout (save_ply) + loss.txt,
+        plus state.npz (Adam moments, iteration) which the reference does not have."""
+        import os
+        from .utils.point_cloud_utils import save_ply
+        ckpt = os.path.join(str(directory), "point_cloud", f"iteration_{iteration}")
+        os.makedirs(ckpt, exist_ok=True)
+        save_ply(self.params.as_dict(), os.path.join(ckpt, "point_cloud.ply"), self.num_points)
+        with open(os.path.join(str(directory), "loss.txt"), "w") as f:
+            for row in self.losses:
+                f.write(f"{row[1] if isinstance(row, tuple) else row}\n")
+        np.savez(os.path.join(ckpt, "state.npz"), iteration=iteration, num_points=self.num_points,
+                 adam_m=self.adam_m.flat.cpu().numpy(), adam_v=self.adam_v.flat.cpu().numpy())
+        return ckpt
+
+    def load_checkpoint(self, ckpt_dir):
+        """Restores parameters (bit-exact: the PLY stores raw float32) and the Adam state; returns the
+        iteration to continue from."""
+        import os
+        from .utils.point_cloud_utils import load_ply
+        params = load_ply(os.path.join(str(ckpt_dir), "point_cloud.ply"))
+        st = np.load(os.path.join(str(ckpt_dir), "state.npz"))
+        self._replace(self._new_flat(int(st["num_points"])).load(params))
+        self.adam_m.flat.copy_(torch.from_numpy(st["adam_m"]))
+        self.adam_v.flat.copy_(torch.from_numpy(st["adam_v"]))
+        return int(st["iteration"]) + 1
+
     # ---- the reference's loop --------------------------------------------------------------------
     def train(self, num_iterations=None, batch_size=1, seed=42, log_every=0):
         """train.py:920-1066 with a seeded camera sampler; losses are read back every ``log_every``

@@ -164,3 +164,24 @@ def test_step_loop_vs_oracle(gs, oracle):
         rel = np.linalg.norm(a - b) / np.linalg.norm(b)
         # Adam's m/sqrt(v) is sign-like: summation-order noise in near-zero gradients flips a few entries
         assert rel <= 5e-3, (k, rel)
+
+
+def test_checkpoint_resume(gs, tmp_path):
+    """Parameters and Adam state survive a save / load bit-exactly; training continues from there."""
+    n, w, h = 2000, 64, 48
+    params, _, _ = gs.scene.synthetic_scene(n, w, h, 0.02, 0.12, seed=3)
+    from gsb200.utils.camera_utils import load_nerf_cameras
+    cams = load_nerf_cameras(w, h)[:4]
+    rng = np.random.default_rng(1)
+    targets = [rng.uniform(0, 1, (h, w, 3)).astype(np.float32) for _ in cams]
+    T = gs.train.Trainer(cams, targets=targets, params=params, config={"num_iterations": 100})
+    for it in range(3):
+        T.train_step(it, [it % 4], densify=False)
+    ckpt = T.save_checkpoint(tmp_path, 2)
+    T2 = gs.train.Trainer(cams, targets=targets, num_points=10, config={"num_iterations": 100})
+    nxt = T2.load_checkpoint(ckpt)
+    assert nxt == 3 and T2.num_points == n
+    assert torch.equal(T2.params.flat, T.params.flat)
+    assert torch.equal(T2.adam_m.flat, T.adam_m.flat) and torch.equal(T2.adam_v.flat, T.adam_v.flat)
+    T2.train_step(nxt, [3], densify=False)
+    assert torch.isfinite(T2.params.flat).all()

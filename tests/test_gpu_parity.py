@@ -145,3 +145,47 @@ def test_torch_inputs_and_column_opacity(gs, oracle):
     kw_t["sh"] = torch.from_numpy(params["shs"]).reshape(-1, 16, 3)
     kw_t["background"] = torch.zeros(3)
     check_forward(gs.forward.render_gaussians(**kw_t), oracle.render_gaussians(**kw))
+
+
+@pytest.mark.parametrize("degree,clamped,bg", [(0, True, (0.0, 0.0, 0.0)), (1, False, (1.0, 1.0, 1.0)),
+                                               (2, True, (0.1, 0.7, 0.3))])
+def test_lower_sh_degrees_vs_oracle(gs, oracle, degree, clamped, bg):
+    """SH degree < 3 (rows keep stride 16), clamped on/off, non-black backgrounds; the reference's
+    own backward is out of bounds here (tests/golden/ref_lego_deg1.npz), the oracle defines it."""
+    params, cam, target = gs.scene.synthetic_scene(5000, 128, 96, 0.01, 0.08, seed=degree + 20)
+    kw = gs.scene.render_kwargs(params, cam, background=bg, degree=degree, clamped=clamped, scale_modifier=0.7)
+    got = gs.forward.render_gaussians(**kw)
+    want = oracle.render_gaussians(**kw)
+    check_forward(got, want)
+    dpix = oracle.compute_image_gradients(want[0], target, lambda_dssim=0)
+    bkw = gs.scene.backward_kwargs(params, cam, got[2], dpix, background=bg, degree=degree, scale_modifier=0.7)
+    okw = gs.scene.backward_kwargs(params, cam, want[2], dpix, background=bg, degree=degree, scale_modifier=0.7)
+    check_grads(gs.backward.backward(**bkw), oracle.backward(**okw))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2])
+def test_tiny_inputs(gs, oracle, n):
+    """Empty and near-empty inputs."""
+    params, cam, target = gs.scene.synthetic_scene(max(n, 1), 48, 32, 0.2, 0.5, seed=1)
+    params = {k: v[: n * (16 if k == "shs" else 1)] for k, v in params.items()}
+    kw = gs.scene.render_kwargs(params, cam, background=(0.2, 0.3, 0.4))
+    got = gs.forward.render_gaussians(**kw)
+    if n == 0:
+        assert got[2]["point_list"].numel() == 0 and not _np(got[0]).any()      # forward.py:830: zeros
+        assert got[2]["radii"].numel() == 0 and tuple(got[0].shape) == (32, 48, 3)
+        return
+    want = oracle.render_gaussians(**kw)
+    check_forward(got, want)
+    dpix = oracle.compute_image_gradients(want[0], target, lambda_dssim=0)
+    check_grads(gs.backward.backward(**gs.scene.backward_kwargs(params, cam, got[2], dpix, background=(0.2, 0.3, 0.4))),
+                oracle.backward(**gs.scene.backward_kwargs(params, cam, want[2], dpix, background=(0.2, 0.3, 0.4))))
+
+
+def test_too_many_rendered_raises_value_error(gs):
+    """forward.py:765-767: more than 2^30 duplicates -> ValueError (here: 70k splats covering all
+    16384 tiles of a 2048x2048 image = 1.15e9 pairs; only the counting pass runs)."""
+    n = 70000
+    params, cam, _ = gs.scene.synthetic_scene(n, 2048, 2048, 40.0, 50.0, seed=2, with_target=False)
+    params["positions"] *= 0.05
+    with pytest.raises(ValueError, match="exceeds the maximum"):
+        gs.forward.render_gaussians(**gs.scene.render_kwargs(params, cam))

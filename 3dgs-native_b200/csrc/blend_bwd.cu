@@ -180,6 +180,281 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core pixel reduction (default).  The per-Gaussian gradients are sums over the pixels of a
+// warp's 4x8 block:  with  s = G * dL_dalpha  and  w = alpha * T  per (pixel, Gaussian),
+//   dL_dcolor[c]           = sum_p w * dL_dpixel[p][c]
+//   dL_dopacity            = sum_p s
+//   dL_dmean2D, dL_dconic  = linear combinations (per-Gaussian coefficients) of the six moments
+//                            sum_p s * {1, i, r, i^2, i*r, r^2},  (i, r) = block-local pixel coords
+// i.e. two small matrix products  [16 Gaussians x 32 pixels] x [32 pixels x 6]  and  x [32 x 3].
+// Each lane stores its s and w for 16 consecutive hits into a per-warp shared-memory tile; the warp
+// then multiplies the tile with the constant pixel matrices on the tensor cores
+// (mma.sync.m16n8k8 TF32, fp32 accumulate; operands split hi + lo so the products carry ~21
+// mantissa bits; the monomials are small integers, exact in TF32) and 16 lanes turn the moments
+// into the nine gradient scalars and issue the REDs.  This replaces the 14-shuffle / 14-select /
+// 14-add butterfly per (warp, Gaussian) -- a third of the old kernel's instructions -- by
+// 2 STS per hit plus ~13 instructions per hit amortised over the group.
+constexpr int kGrp = 16;   // hits per MMA group (the M dimension)
+constexpr int kSRow = 36;  // padded row length (floats) of the S / W tiles: conflict-free 16-byte reads
+constexpr int kDRow = 12;  // row length of the result tile (6 moments, 2 pad, 3 colours, 1 pad)
+
+struct BwdSmem {
+  float4 a[256];   // x, y, conic.a, conic.b
+  float4 b[256];   // conic.c, opacity, power threshold, position in the tile's list (int bits)
+  float4 c[256];   // r, g, b, gid (int bits)
+  int2 meta[256];  // position in the tile's list, block mask
+  int smax[8];
+  int wcnt[8];
+  unsigned char widx[8][256];     // per warp: the staged entries it has to replay
+  float sw[8][2][kGrp][kSRow];    // per warp: S tile (s per hit x pixel), W tile; the S tile is reused for results
+};
+
+// TF32 head of x (mantissa truncated to 10 bits: one LOP3; cvt.rna.tf32 costs four instructions on
+// sm_100a).  x - tf32_hi(x) is exact, so hi + lo carries >= 20 mantissa bits through the MMA.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; x must be a normal number
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// D[16x8] += A[16x8] * B[8x8], TF32 inputs, fp32 accumulate.  Fragment layout (PTX ISA, m16n8k8):
+//   A: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  B: b0 (k=t, n=g)  b1 (k=t+4, n=g);
+//   D: d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)      with g = lane >> 2, t = lane & 3
+__device__ __forceinline__ void mma_tf32(float d[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// D[16x8] += A[16x4] * B[4x8] (m16n8k4): A: a0 (g, t) a1 (g+8, t);  B: b0 (k=t, n=g);  D as above.
+__device__ __forceinline__ void mma_tf32_k4(float d[4], float a0, float a1, float b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(b0)));
+}
+
+__device__ __forceinline__ float f4_get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+template <int MINB>  // resident CTAs per SM the register budget is cut for: 3 (80 registers) or 4 (64)
+__global__ void __launch_bounds__(256, MINB)
+blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
+                          const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                          const float* __restrict__ rgb, const float* __restrict__ final_T,
+                          const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+                          float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
+                          float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor) {
+  constexpr int NT = 256, NW = 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  const int tile_id = tile_y * P.grid_x + tile_x;
+  const int bx0 = tile_x * kTile + (warp & 1) * 8, by0 = tile_y * kTile + (warp >> 1) * 4;  // block origin
+  const int px = bx0 + (lane & 7);
+  const int py = by0 + (lane >> 3);
+  const float pxf = (float)px, pyf = (float)py;
+  const int2 range = ranges[tile_id];
+  const unsigned my_mask = gs_warp_mask(warp);
+  const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
+
+  const bool inside = (px < P.W && py < P.H);
+  const size_t pix = inside ? ((size_t)py * P.W + px) : 0;
+  const float T_final = inside ? final_T[pix] : 0.0f;
+  float T = T_final;
+  // backward.py:619 last_kept = min(range_end, range_start + n_contrib), relative to range_start
+  const int kept = inside ? min(range.y - range.x, n_contrib[pix]) : 0;
+  const float dp0 = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
+  const float dp1 = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
+  const float dp2 = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
+  const float bgdot = gs_dot3(P.bg0, P.bg1, P.bg2, dp0, dp1, dp2);  // backward.py:679
+  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, last_alpha = 0.0f, lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;
+
+  // Constant B fragments.  Logical column (kk, t) / (kk, t+4) of k-step kk is the pixel owned by
+  // lane 8t + kk / 8t + 4 + kk (block coords i = kk or 4 + kk, r = t), so that a lane's A operands
+  // for the four k-steps are two contiguous float4 of a tile row.
+  const int fg = lane >> 2, ft = lane & 3;
+  // monomial column fg of pixel (i, r = ft) as  m0 + i * (m1 + i * m2):  1, i, r, i^2, i*r, r^2, 0, 0
+  const float fr = (float)ft;
+  const float m0 = fg == 0 ? 1.0f : fg == 2 ? fr : fg == 5 ? fr * fr : 0.0f;
+  const float m1 = fg == 1 ? 1.0f : fg == 4 ? fr : 0.0f;
+  const float m2 = fg == 3 ? 1.0f : 0.0f;
+  // dL_dpixels as a B operand: column fg < 3 of pixel (i, r = ft); re-read (L1) at every group
+  // rather than held in 16 registers.  Pixels outside the image read pixel 0 and are zeroed.
+  const bool dp_row_ok = fg < 3 && (by0 + ft) < P.H;
+  const float* const dp_row = dL_dpixels + (dp_row_ok ? 3 * ((size_t)(by0 + ft) * P.W + bx0) + fg : 0);
+  const int dp_cols = dp_row_ok ? min(8, P.W - bx0) : 0;  // valid i are 0 .. dp_cols-1
+
+  const int my_max = __reduce_max_sync(0xffffffffu, kept);
+  if (lane == 0) sm.smax[warp] = my_max;
+  __syncthreads();
+  int tile_max = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) tile_max = max(tile_max, sm.smax[w]);
+
+  const float ddelx_dx = 0.5f * (float)P.W;
+  const float ddely_dy = 0.5f * (float)P.H;
+  float* const tS = &sm.sw[warp][0][0][0];
+  float* const tW = &sm.sw[warp][1][0][0];
+  const unsigned char* const wlist = sm.widx[warp];
+
+  for (int hi = tile_max; hi > 0; hi -= NT) {
+    const int n_in = min(NT, hi);
+    __syncthreads();
+    float4 ea, eb, ec;
+    unsigned bmask = 0u;
+    if (tid < n_in) {
+      const int gid = point_list[range.x + hi - 1 - tid];
+      const float2 p = xy[gid];
+      const float4 co = conic_opacity[gid];
+      const float thr = gs_power_threshold(co.w);
+      bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
+      ea = make_float4(p.x, p.y, co.x, co.y);
+      eb = make_float4(co.z, co.w, thr, __int_as_float(hi - 1 - tid));
+      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
+    }
+    int cnt;
+    const int slot = compact_slot<NW>(bmask != 0u, lane, warp, sm.wcnt, cnt);
+    if (bmask != 0u) {
+      sm.a[slot] = ea;
+      sm.b[slot] = eb;
+      sm.c[slot] = ec;
+      sm.meta[slot] = make_int2(hi - 1 - tid, (int)bmask);
+    }
+    __syncthreads();
+    // a warp whose pixels all stopped before this batch has nothing to do in it
+    if (my_max <= hi - n_in) continue;
+    // entries that touch this warp's block and lie inside its replay range (position < my_max)
+    const int wn = warp_compact_hits(sm.meta, cnt, my_mask, my_max, lane, sm.widx[warp]);
+    unsigned anybits = 0u;
+    int gslot = 0;              // slot of hit q in the current group
+    float* pS = tS + lane;      // this lane's column of the S tile, row gslot (the W tile is 16 rows further)
+    for (int q = 0; q < wn; ++q) {
+      const int j = wlist[q];
+      const float4 a = sm.a[j];
+      const float4 b = sm.b[j];
+      const float dx = a.x - pxf;
+      const float dy = a.y - pyf;
+      float sv = 0.0f, wv = 0.0f;
+      bool any = false;
+      const float power = gs_power(a.z, a.w, b.x, dx, dy);
+      // the replay limit (pixel replays the entry iff position < kept), backward.py:647 (power > 0)
+      // and the conservative exponent threshold
+      if (__float_as_int(b.w) < kept && !(power > 0.0f) && !(power < b.z)) {
+        const float G = gs_expf(power);
+        const float alpha = f_min(0.99f, b.y * G);
+        if (!(alpha < (1.0f / 255.0f))) {  // backward.py:655
+          const float4 c = sm.c[j];
+          const float inv_1ma = rcp_approx(1.0f - alpha);      // backward.py:658,680; 1 - alpha is in [0.01, 1]
+          T = T * inv_1ma;
+          acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
+          acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
+          acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
+          lc0 = c.x;
+          lc1 = c.y;
+          lc2 = c.z;
+          float dL_dalpha = gs_dot3(c.x - acc0, c.y - acc1, c.z - acc2, dp0, dp1, dp2);
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final * inv_1ma) * bgdot;
+          wv = alpha * T;          // d(channel)/d(colour), backward.py:672
+          sv = G * dL_dalpha;      // dL_dG = opacity * dL_dalpha is applied after the reduction
+          any = true;
+        }
+      }
+      pS[0] = sv;
+      pS[kGrp * kSRow] = wv;
+      if (__any_sync(0xffffffffu, any)) anybits |= 1u << gslot;
+      if (gslot != kGrp - 1 && q != wn - 1) {
+        ++gslot;
+        pS += kSRow;
+        continue;
+      }
+
+      // ---- group complete: reduce its (up to) 16 hits over the 32 pixels on the tensor cores ----
+      __syncwarp();
+      float dm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // k-step ks (m16n8k4) covers the pixels (i = ks, r = 0..3); lane (fg, ft) supplies rows fg, fg + 8
+      // at pixel 8 ft + ks: two float4 per half row serve four k-steps.
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float4 va = *reinterpret_cast<const float4*>(tS + fg * kSRow + 8 * ft + 4 * half);
+        const float4 vb = *reinterpret_cast<const float4*>(tS + (fg + 8) * kSRow + 8 * ft + 4 * half);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ks = (float)(4 * half + e);
+          const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
+          const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
+          const float b0 = m0 + ks * (m1 + ks * m2);
+          mma_tf32_k4(dm, h0, h1, b0);
+          mma_tf32_k4(dm, a0 - h0, a1 - h1, b0);
+        }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float4 va = *reinterpret_cast<const float4*>(tW + fg * kSRow + 8 * ft + 4 * half);
+        const float4 vb = *reinterpret_cast<const float4*>(tW + (fg + 8) * kSRow + 8 * ft + 4 * half);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * half + e;
+          const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
+          const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
+          const float dpv = (i < dp_cols) ? __ldg(dp_row + 3 * i) : 0.0f;
+          const float p0 = tf32_hi(dpv);
+          mma_tf32_k4(dc, h0, h1, p0);
+          mma_tf32_k4(dc, a0 - h0, a1 - h1, p0);
+          mma_tf32_k4(dc, h0, h1, dpv - p0);
+        }
+      }
+      __syncwarp();  // every lane has read its operands: the S tile may now take the results
+      *reinterpret_cast<float2*>(tS + fg * kDRow + 2 * ft) = make_float2(dm[0], dm[1]);
+      *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 2 * ft) = make_float2(dm[2], dm[3]);
+      if (ft < 2) {
+        *reinterpret_cast<float2*>(tS + fg * kDRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
+        *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
+      }
+      __syncwarp();
+      if (lane <= gslot && ((anybits >> lane) & 1u)) {
+        const int je = wlist[q - gslot + lane];
+        const float4 ga = sm.a[je];
+        const float4 gb = sm.b[je];
+        const int gid = __float_as_int(sm.c[je].w);
+        const float4 m03 = *reinterpret_cast<const float4*>(tS + lane * kDRow);
+        const float2 m45 = *reinterpret_cast<const float2*>(tS + lane * kDRow + 4);
+        const float4 col = *reinterpret_cast<const float4*>(tS + lane * kDRow + 8);
+        const float ux = ga.x - (float)bx0, uy = ga.y - (float)by0;   // dx = ux - i, dy = uy - r
+        const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
+        const float Sdx = ux * S0 - Si;
+        const float Sdy = uy * S0 - Sr;
+        const float Sdxx = ux * (Sdx - Si) + Sii;
+        const float Sdxy = ux * Sdy - uy * Si + Sir;
+        const float Sdyy = uy * (Sdy - Sr) + Srr;
+        const float o = gb.y;  // dL_dG = opacity * dL_dalpha (backward.py:683)
+        atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
+        atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
+        atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
+        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, -o * (ga.z * Sdx + ga.w * Sdy) * ddelx_dx);   // backward.py:691-695
+        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, -o * (gb.x * Sdy + ga.w * Sdx) * ddely_dy);
+        atomicAdd(dL_dconic + 4 * (size_t)gid + 0, -0.5f * o * Sdxx);                              // backward.py:698-703
+        atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * o * Sdxy);
+        atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * o * Sdyy);
+        atomicAdd(dL_dopacity + gid, S0);                                                           // backward.py:706
+      }
+      __syncwarp();  // results consumed before the next group overwrites the tile
+      anybits = 0u;
+      gslot = 0;
+      pS = tS + lane;
+    }
+  }
+}
+
 }  // namespace
 
 GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const int32_t* ranges,
@@ -198,8 +473,30 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
   GSB_CUDA(ctx, cudaMemsetAsync(dL_dcolor, 0, sizeof(float) * 3 * (size_t)n, s));
   BlendParams P = make_blend_params(f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  GSB_LAUNCH(ctx, blend_backward_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
-             reinterpret_cast<const float2*>(points_xy), reinterpret_cast<const float4*>(conic_opacity), rgb, final_T,
-             n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+  if (g_bwd_reduce == 0) {  // A/B: warp-shuffle butterfly reduction
+    GSB_LAUNCH(ctx, blend_backward_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
+               reinterpret_cast<const float2*>(points_xy), reinterpret_cast<const float4*>(conic_opacity), rgb, final_T,
+               n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+    return GSB_OK;
+  }
+  static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in, once per process
+  if (!attr_set) {
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem)));
+    attr_set = true;
+  }
+  if (g_bwd_reduce == 2) {
+    GSB_LAUNCH(ctx, blend_backward_mma_kernel<4>, grid, 256, sizeof(BwdSmem), s, P,
+               reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
+               reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
+               dL_dconic, dL_dopacity, dL_dcolor);
+  } else {
+    GSB_LAUNCH(ctx, blend_backward_mma_kernel<3>, grid, 256, sizeof(BwdSmem), s, P,
+               reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
+               reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
+               dL_dconic, dL_dopacity, dL_dcolor);
+  }
   return GSB_OK;
 }

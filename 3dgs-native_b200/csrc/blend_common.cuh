@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 extern int g_blend_cull;
+extern int g_bwd_reduce;
 
 namespace {
 

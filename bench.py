@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--cull", type=int, default=1)
+    ap.add_argument("--bwd-reduce", type=int, default=1, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -284,6 +285,7 @@ def ours(args):
     T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=args.exchange,
                       config={"num_iterations": 7000, "lr_scheduler_config": lrs})
     T.ctx.set_option("blend_cull", args.cull)
+    T.ctx.set_option("bwd_reduce", args.bwd_reduce)
 
     def batch(it):   # one view per rank per step, cycling through the poses
         return [(it * world + r) % N_CAMERAS for r in range(world)]

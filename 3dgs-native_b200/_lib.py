@@ -43,11 +43,11 @@ _SIGS = {
     "gsb_sort_pairs64": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int]),
     "gsb_tile_ranges": (C.c_int, [vp, vp, i64, vp, i32, vp]),
     "gsb_bin_by_tile": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, C.POINTER(i64), C.POINTER(i32)]),
-    "gsb_blend_forward": (C.c_int, [vp, vp, C.POINTER(Frame)] + [vp] * 10),
-    "gsb_forward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 14 + [i64] + [vp] * 5 + [C.POINTER(i64)]),
-    "gsb_blend_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 12),
+    "gsb_blend_forward": (C.c_int, [vp, vp, C.POINTER(Frame)] + [vp] * 11),
+    "gsb_forward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 14 + [i64] + [vp] * 5 + [C.POINTER(i64), vp]),
+    "gsb_blend_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 13),
     "gsb_preprocess_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 15),
-    "gsb_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 25),
+    "gsb_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 26),
     "gsb_adam_step": (C.c_int, [vp, vp, i32] + [vp] * 5 + [f32] * 8 + [i32] + [vp] * 15),
     "gsb_flat_layout": (C.c_int, [i32, C.POINTER(i64), C.POINTER(i64)]),
     "gsb_adam_step_peers": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64,

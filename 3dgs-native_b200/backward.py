@@ -32,6 +32,10 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
     final_Ts = td(img_buffer.get("final_Ts"))
     n_contrib = td(img_buffer.get("n_contrib"), i32)
     point_list = td(binning_buffer.get("point_list"), i32)
+    block_masks = binning_buffer.get("block_masks")   # optional extra of our forward (same point_list)
+    block_masks = td(block_masks, i32) if block_masks is not None else None
+    if block_masks is not None and block_masks.numel() != point_list.numel():
+        raise ValueError("binning_buffer['block_masks'] must have one entry per point_list entry")
     if geom_buffer is not None:  # backward.py:1092-1103
         radii = geom_buffer.get("radii") if radii is None else radii
         means2D = geom_buffer.get("means2D") if means2D is None else means2D
@@ -61,6 +65,7 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
                                  p(scl), p(rot), p(radii_t), p(xy), p(con_o), p(colors), p(clamped_state), p(cov3),
                                  p(point_list), p(ranges), p(final_Ts), p(n_contrib), p(dpix), p(g["dL_dmean3D"]),
                                  p(g["dL_dcolor"]), p(g["dL_dshs"]), p(g["dL_dopacity"]), p(g["dL_dscale"]),
-                                 p(g["dL_drot"]), p(g["dL_dmean2D"]), p(g["dL_dconic"]), p(g["dL_dcov3D"]))
+                                 p(g["dL_drot"]), p(g["dL_dmean2D"]), p(g["dL_dconic"]), p(g["dL_dcov3D"]),
+                                 p(block_masks))
     ctx.check(rc)
     return g

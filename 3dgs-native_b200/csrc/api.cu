@@ -216,7 +216,7 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
                         int32_t* radii, int32_t* point_offsets, float* points_xy, float* depths, float* rgb,
                         float* cov3Ds, float* conic_opacity, float* clamped_state, int32_t* point_list,
                         int64_t point_list_capacity, int32_t* ranges, float* image, float* inv_depth, float* final_T,
-                        int32_t* n_contrib, int64_t* num_rendered_host) {
+                        int32_t* n_contrib, int64_t* num_rendered_host, int32_t* block_masks) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && n >= 0 && f->width > 0 && f->height > 0, "gsb_forward: bad frame or n");
   cudaStream_t s = (cudaStream_t)s_;
@@ -250,7 +250,7 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   }
   // forward.py:844-863 (+ the no-op track_pixel_stats of 867-879)
   return gsb_blend_forward(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
-                           final_T, n_contrib);
+                           final_T, n_contrib, block_masks);
 }
 
 GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
@@ -260,7 +260,7 @@ GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_
                          const int32_t* ranges, const float* final_T, const int32_t* n_contrib,
                          const float* dL_dpixels, float* dL_dmean3D, float* dL_dcolor, float* dL_dshs,
                          float* dL_dopacity, float* dL_dscale, float* dL_drot, float* dL_dmean2D, float* dL_dconic,
-                         float* dL_dcov3D) {
+                         float* dL_dcov3D, const int32_t* block_masks) {
   (void)opacities;  // converted and unused by the reference as well (backward.py:1056)
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && n >= 0, "gsb_backward: bad frame or n");
@@ -270,7 +270,7 @@ GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_
   if ((rc = reserve_per_gaussian(ctx, s, n)) != GSB_OK) return rc;
   // backward.py:1135-1152
   rc = gsb_blend_backward(ctx, s_, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
-                          dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+                          dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, block_masks);
   if (rc != GSB_OK) return rc;
   // backward.py:1155-1182
   rc = gsb_preprocess_backward(ctx, s_, f, n, means, radii, shs, scales, rotations, cov3Ds, clamped_state, dL_dmean2D,

@@ -30,36 +30,46 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+struct FwdSmem {
+  float4 a[256];   // x, y, conic.a, conic.b
+  float4 b[256];   // conic.c, opacity, power threshold, 1/depth
+  float4 c[256];   // r, g, b, 1-based position in the tile's list (int bits)
+  int2 meta[256];  // 1-based position, block mask (read by the per-warp compaction)
+  int wcnt[8];
+  unsigned char widx[8][256];  // per warp: the staged entries that touch its block
+};
+
+__global__ void __launch_bounds__(256, 5)
 blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
                      const float2* __restrict__ xy, const float* __restrict__ rgb,
                      const float4* __restrict__ conic_opacity, const float* __restrict__ depths,
                      float* __restrict__ image, float* __restrict__ inv_depth, float* __restrict__ final_T,
-                     int* __restrict__ n_contrib) {
+                     int* __restrict__ n_contrib, unsigned* __restrict__ block_masks) {
   constexpr int NT = 256, NW = 8;
-  __shared__ float4 s_a[NT];   // x, y, conic.a, conic.b
-  __shared__ float4 s_b[NT];   // conic.c, opacity, power threshold, 1/depth
-  __shared__ float4 s_c[NT];   // r, g, b, -
-  __shared__ int2 s_meta[NT];  // 1-based position in the tile's list, block mask
-  __shared__ int s_wcnt[NW];
-  __shared__ unsigned char s_widx[NW][NT];  // per warp: the staged entries that touch its block
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int tile_id = tile_y * P.grid_x + tile_x;
   const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
   const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
-  const float pxf = (float)px, pyf = (float)py;
+  // A finished pixel (outside the image, or T ran out) gets a NaN x coordinate: its exponent is
+  // then NaN and fails the range test below, so the inner loop needs no separate `done` test.
+  float pxf = (float)px;
+  const float pyf = (float)py;
   const unsigned my_mask = gs_warp_mask(warp);
   const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
   const bool inside = (px < P.W && py < P.H);
 
   bool done = !inside;
+  if (done) pxf = __int_as_float(0x7fc00000);
   float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dp = 0.0f;
   int last = 0;
 
   const int2 range = ranges[tile_id];
   const int todo = range.y - range.x;
+  const unsigned char* const wlist = sm.widx[warp];
   for (int base = 0; base < todo; base += NT) {
     if (__syncthreads_and(done)) break;
     float4 ea, eb, ec;
@@ -70,45 +80,50 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
       const float4 co = conic_opacity[gid];
       const float thr = gs_power_threshold(co.w);
       bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
+      if (block_masks) block_masks[range.x + base + tid] = bmask;  // handed on to the backward
       ea = make_float4(p.x, p.y, co.x, co.y);
       eb = make_float4(co.z, co.w, thr, 1.0f / depths[gid]);
-      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], 0.0f);
+      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(base + tid + 1));
     }
     int cnt;
-    const int slot = compact_slot<NW>(bmask != 0u, lane, warp, s_wcnt, cnt);
+    const int slot = compact_slot<NW>(bmask != 0u, lane, warp, sm.wcnt, cnt);
     if (bmask != 0u) {
-      s_a[slot] = ea;
-      s_b[slot] = eb;
-      s_c[slot] = ec;
-      s_meta[slot] = make_int2(base + tid + 1, (int)bmask);
+      sm.a[slot] = ea;
+      sm.b[slot] = eb;
+      sm.c[slot] = ec;
+      sm.meta[slot] = make_int2(base + tid + 1, (int)bmask);
     }
     __syncthreads();
     if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are all finished
-    const int wn = warp_compact_hits(s_meta, cnt, my_mask, 0x7fffffff, lane, s_widx[warp]);
+    const int wn = warp_compact_hits(sm.meta, cnt, my_mask, 0x7fffffff, lane, sm.widx[warp]);
     for (int q = 0; q < wn; ++q) {
-      if (done) continue;
-      const int j = s_widx[warp][q];
-      const float4 a = s_a[j];
-      const float4 b = s_b[j];
+      const int j = wlist[q];
+      const float4 a = sm.a[j];
+      const float4 b = sm.b[j];
       const float dx = a.x - pxf;
       const float dy = a.y - pyf;
       const float power = gs_power(a.z, a.w, b.x, dx, dy);
-      if (power > 0.0f) continue;        // forward.py:474
-      if (power < b.z) continue;         // provably alpha < 1/255 (see gs_power_threshold)
+      // forward.py:474 skips power > 0; power < b.z is provably alpha < 1/255 (gs_power_threshold);
+      // written so that the NaN of a finished pixel is skipped too
+      if (!(power <= 0.0f) || !(power >= b.z)) continue;
       const float alpha = f_min(0.99f, b.y * gs_expf(power));
       if (alpha < (1.0f / 255.0f)) continue;
       const float test_T = T * (1.0f - alpha);
       if (test_T < 0.0001f) {            // forward.py:487: the breaking Gaussian is not counted
         done = true;
+        pxf = __int_as_float(0x7fc00000);
         continue;
       }
-      const float4 c = s_c[j];
-      C0 += c.x * alpha * T;
-      C1 += c.y * alpha * T;
-      C2 += c.z * alpha * T;
-      Dp += b.w * alpha * T;
+      // Colour / depth sums are tolerance-compared (1e-4): one product alpha*T and an FMA per
+      // channel.  T, alpha and every decision above keep the exact operation order of the contract.
+      const float4 c = sm.c[j];
+      const float w = alpha * T;
+      C0 = __fmaf_rn(c.x, w, C0);
+      C1 = __fmaf_rn(c.y, w, C1);
+      C2 = __fmaf_rn(c.z, w, C2);
+      Dp = __fmaf_rn(b.w, w, Dp);
       T = test_T;
-      last = s_meta[j].x;
+      last = __float_as_int(c.w);
     }
   }
 
@@ -128,15 +143,15 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
 GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* rgb,
                               const float* conic_opacity, const float* depths, float* image, float* inv_depth,
-                              float* final_T, int32_t* n_contrib) {
+                              float* final_T, int32_t* n_contrib, int32_t* block_masks) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0, "gsb_blend_forward: bad frame");
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_forward: conic_opacity must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)s_;
   BlendParams P = make_blend_params(f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  GSB_LAUNCH(ctx, blend_forward_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
+  GSB_LAUNCH(ctx, blend_forward_kernel, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges), point_list,
              reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity), depths,
-             image, inv_depth, final_T, n_contrib);
+             image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks));
   return GSB_OK;
 }

@@ -56,7 +56,7 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
                       const float* __restrict__ rgb, const float* __restrict__ final_T,
                       const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
-                      float* __restrict__ dL_dcolor) {
+                      float* __restrict__ dL_dcolor, const unsigned* __restrict__ block_masks) {
   constexpr int NT = 256, NW = 8;
   __shared__ float4 s_a[NT];   // x, y, conic.a, conic.b
   __shared__ float4 s_b[NT];   // conic.c, opacity, power threshold, -
@@ -104,14 +104,20 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
     float4 ea, eb, ec;
     unsigned bmask = 0u;
     if (tid < n_in) {
-      const int gid = point_list[range.x + hi - 1 - tid];
-      const float2 p = xy[gid];
-      const float4 co = conic_opacity[gid];
-      const float thr = gs_power_threshold(co.w);
-      bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
-      ea = make_float4(p.x, p.y, co.x, co.y);
-      eb = make_float4(co.z, co.w, thr, 0.0f);
-      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
+      const int e = range.x + hi - 1 - tid;
+      // the forward's culling mask when it was handed on, else recomputed below (same value)
+      const bool have = P.cull && block_masks != nullptr;
+      bmask = have ? block_masks[e] : 0xffffffffu;
+      if (bmask != 0u) {
+        const int gid = point_list[e];
+        const float2 p = xy[gid];
+        const float4 co = conic_opacity[gid];
+        const float thr = gs_power_threshold(co.w);
+        if (P.cull && !have) bmask = gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0);
+        ea = make_float4(p.x, p.y, co.x, co.y);
+        eb = make_float4(co.z, co.w, thr, 0.0f);
+        ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
+      }
     }
     int cnt;
     const int slot = compact_slot<NW>(bmask != 0u, lane, warp, s_wcnt, cnt);
@@ -249,7 +255,8 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
                           const float* __restrict__ rgb, const float* __restrict__ final_T,
                           const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                           float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
-                          float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor) {
+                          float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
+                          const unsigned* __restrict__ block_masks) {
   constexpr int NT = 256, NW = 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -311,14 +318,20 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     float4 ea, eb, ec;
     unsigned bmask = 0u;
     if (tid < n_in) {
-      const int gid = point_list[range.x + hi - 1 - tid];
-      const float2 p = xy[gid];
-      const float4 co = conic_opacity[gid];
-      const float thr = gs_power_threshold(co.w);
-      bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
-      ea = make_float4(p.x, p.y, co.x, co.y);
-      eb = make_float4(co.z, co.w, thr, __int_as_float(hi - 1 - tid));
-      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
+      const int e = range.x + hi - 1 - tid;
+      // the forward's culling mask when it was handed on, else recomputed below (same value)
+      const bool have = P.cull && block_masks != nullptr;
+      bmask = have ? block_masks[e] : 0xffffffffu;
+      if (bmask != 0u) {
+        const int gid = point_list[e];
+        const float2 p = xy[gid];
+        const float4 co = conic_opacity[gid];
+        const float thr = gs_power_threshold(co.w);
+        if (P.cull && !have) bmask = gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0);
+        ea = make_float4(p.x, p.y, co.x, co.y);
+        eb = make_float4(co.z, co.w, thr, __int_as_float(hi - 1 - tid));
+        ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
+      }
     }
     int cnt;
     const int slot = compact_slot<NW>(bmask != 0u, lane, warp, sm.wcnt, cnt);
@@ -333,7 +346,6 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     if (my_max <= hi - n_in) continue;
     // entries that touch this warp's block and lie inside its replay range (position < my_max)
     const int wn = warp_compact_hits(sm.meta, cnt, my_mask, my_max, lane, sm.widx[warp]);
-    unsigned anybits = 0u;
     int gslot = 0;              // slot of hit q in the current group
     float* pS = tS + lane;      // this lane's column of the S tile, row gslot (the W tile is 16 rows further)
     for (int q = 0; q < wn; ++q) {
@@ -343,7 +355,6 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       const float dx = a.x - pxf;
       const float dy = a.y - pyf;
       float sv = 0.0f, wv = 0.0f;
-      bool any = false;
       const float power = gs_power(a.z, a.w, b.x, dx, dy);
       // the replay limit (pixel replays the entry iff position < kept), backward.py:647 (power > 0)
       // and the conservative exponent threshold
@@ -366,12 +377,10 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
           dL_dalpha += (-T_final * inv_1ma) * bgdot;
           wv = alpha * T;          // d(channel)/d(colour), backward.py:672
           sv = G * dL_dalpha;      // dL_dG = opacity * dL_dalpha is applied after the reduction
-          any = true;
         }
       }
       pS[0] = sv;
       pS[kGrp * kSRow] = wv;
-      if (__any_sync(0xffffffffu, any)) anybits |= 1u << gslot;
       if (gslot != kGrp - 1 && q != wn - 1) {
         ++gslot;
         pS += kSRow;
@@ -421,14 +430,18 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
         *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
       }
       __syncwarp();
-      if (lane <= gslot && ((anybits >> lane) & 1u)) {
+      const float4 m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow);
+      const float2 m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kDRow + 4);
+      const float4 col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow + 8);
+      // a hit none of the 32 pixels used sums to nine exact zeros: adding them would be a no-op
+      const unsigned nz = (__float_as_uint(m03.x) | __float_as_uint(m03.y) | __float_as_uint(m03.z) |
+                           __float_as_uint(m03.w) | __float_as_uint(m45.x) | __float_as_uint(m45.y) |
+                           __float_as_uint(col.x) | __float_as_uint(col.y) | __float_as_uint(col.z)) << 1;
+      if (lane <= gslot && nz != 0u) {
         const int je = wlist[q - gslot + lane];
         const float4 ga = sm.a[je];
         const float4 gb = sm.b[je];
         const int gid = __float_as_int(sm.c[je].w);
-        const float4 m03 = *reinterpret_cast<const float4*>(tS + lane * kDRow);
-        const float2 m45 = *reinterpret_cast<const float2*>(tS + lane * kDRow + 4);
-        const float4 col = *reinterpret_cast<const float4*>(tS + lane * kDRow + 8);
         const float ux = ga.x - (float)bx0, uy = ga.y - (float)by0;   // dx = ux - i, dy = uy - r
         const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
         const float Sdx = ux * S0 - Si;
@@ -448,7 +461,6 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
         atomicAdd(dL_dopacity + gid, S0);                                                           // backward.py:706
       }
       __syncwarp();  // results consumed before the next group overwrites the tile
-      anybits = 0u;
       gslot = 0;
       pS = tS + lane;
     }
@@ -461,7 +473,7 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
                                const int32_t* point_list, const float* points_xy, const float* conic_opacity,
                                const float* rgb, const float* final_T, const int32_t* n_contrib,
                                const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
-                               float* dL_dcolor) {
+                               float* dL_dcolor, const int32_t* block_masks) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0 && n >= 0, "gsb_blend_backward: bad frame");
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_backward: conic_opacity must be 16-byte aligned");
@@ -473,10 +485,11 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
   GSB_CUDA(ctx, cudaMemsetAsync(dL_dcolor, 0, sizeof(float) * 3 * (size_t)n, s));
   BlendParams P = make_blend_params(f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
+  const unsigned* masks = reinterpret_cast<const unsigned*>(block_masks);
   if (g_bwd_reduce == 0) {  // A/B: warp-shuffle butterfly reduction
     GSB_LAUNCH(ctx, blend_backward_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
                reinterpret_cast<const float2*>(points_xy), reinterpret_cast<const float4*>(conic_opacity), rgb, final_T,
-               n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+               n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, masks);
     return GSB_OK;
   }
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in, once per process
@@ -491,12 +504,12 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
     GSB_LAUNCH(ctx, blend_backward_mma_kernel<4>, grid, 256, sizeof(BwdSmem), s, P,
                reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
                reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
-               dL_dconic, dL_dopacity, dL_dcolor);
+               dL_dconic, dL_dopacity, dL_dcolor, masks);
   } else {
     GSB_LAUNCH(ctx, blend_backward_mma_kernel<3>, grid, 256, sizeof(BwdSmem), s, P,
                reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
                reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
-               dL_dconic, dL_dopacity, dL_dcolor);
+               dL_dconic, dL_dopacity, dL_dcolor, masks);
   }
   return GSB_OK;
 }

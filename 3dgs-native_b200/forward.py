@@ -54,14 +54,14 @@ def render_gaussians(background, means3D, colors=None, opacity=None, scales=None
     D = C.c_int64(0)
     cap = max(ctx.capacity_hint, 4 * n, 1024)
     for _attempt in range(2):
-        point_list = e(cap, dtype=i32)
+        point_list, block_masks = e(cap, dtype=i32), e(cap, dtype=i32)
         rc = L.gsb_forward(ctx.h, _lib.stream_ptr(ctx.device_index), C.byref(frame), n, _lib.ptr(means), _lib.ptr(scl),
                            _lib.ptr(rot), _lib.ptr(opac), _lib.ptr(shs), _lib.ptr(out["radii"]),
                            _lib.ptr(out["point_offsets"]), _lib.ptr(out["points_xy_image"]), _lib.ptr(out["depths"]),
                            _lib.ptr(out["colors"]), _lib.ptr(out["cov3Ds"]), _lib.ptr(out["conic_opacity"]),
                            _lib.ptr(out["clamped_state"]), _lib.ptr(point_list), cap, _lib.ptr(out["ranges"]),
                            _lib.ptr(image), _lib.ptr(depth), _lib.ptr(out["final_Ts"]), _lib.ptr(out["n_contrib"]),
-                           C.byref(D))
+                           C.byref(D), _lib.ptr(block_masks))
         if rc == _lib.GSB_ERR_CAPACITY:
             cap = int(D.value) + int(D.value) // 8 + 1024
             continue
@@ -69,4 +69,8 @@ def render_gaussians(background, means3D, colors=None, opacity=None, scales=None
         break
     ctx.capacity_hint = max(ctx.capacity_hint, int(D.value) + int(D.value) // 8)
     out["point_list"] = point_list[: int(D.value)]
-    return image, depth, {k: out[k] for k in _KEYS}
+    res = {k: out[k] for k in _KEYS}
+    # not a reference key: the tile kernels' per-entry culling masks; backward() reuses them when the
+    # dict is passed on as binning_buffer, and recomputes them when the key is absent
+    res["block_masks"] = block_masks[: int(D.value)]
+    return image, depth, res

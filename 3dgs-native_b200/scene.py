@@ -113,6 +113,6 @@ def backward_kwargs(params, cam, buffers, dL_dpixels, background=(0.0, 0.0, 0.0)
                 radii=buffers["radii"], means2D=buffers["points_xy_image"],
                 conic_opacity=buffers["conic_opacity"], rgb=buffers["colors"], cov3Ds=buffers["cov3Ds"],
                 clamped=buffers["clamped_state"], geom_buffer=geom,
-                binning_buffer={"point_list": buffers["point_list"]},
+                binning_buffer={k: buffers[k] for k in ("point_list", "block_masks") if k in buffers},
                 img_buffer={"ranges": buffers["ranges"], "final_Ts": buffers["final_Ts"],
                             "n_contrib": buffers["n_contrib"]}, degree=degree, debug=False)

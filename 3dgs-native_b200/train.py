@@ -102,7 +102,7 @@ class FrameBuffers:
         self.ranges = e(gx * gy, 2, dtype=i32)
         self.final_T, self.n_contrib = e(height, width), e(height, width, dtype=i32)
         self.image, self.depth = e(height, width, 3), e(height, width)
-        self.point_list = e(capacity, dtype=i32)
+        self.point_list, self.block_masks = e(capacity, dtype=i32), e(capacity, dtype=i32)
         self.capacity = capacity
         self.num_rendered = 0
         self.dpix = e(height, width, 3)
@@ -216,10 +216,12 @@ class Trainer:
                                p(P["positions"]), p(P["scales"]), p(P["rotations"]), p(P["opacities"]), p(P["shs"]),
                                p(fb.radii), p(fb.point_offsets), p(fb.xy), p(fb.depths), p(fb.colors), p(fb.cov3Ds),
                                p(fb.conic_opacity), p(fb.clamped_state), p(fb.point_list), fb.capacity, p(fb.ranges),
-                               p(fb.image), p(fb.depth), p(fb.final_T), p(fb.n_contrib), C.byref(D))
+                               p(fb.image), p(fb.depth), p(fb.final_T), p(fb.n_contrib), C.byref(D),
+                               p(fb.block_masks))
             if rc == _lib.GSB_ERR_CAPACITY:
                 fb.capacity = int(D.value) + int(D.value) // 8 + 1024
                 fb.point_list = torch.empty(fb.capacity, dtype=torch.int32, device=self.device)
+                fb.block_masks = torch.empty(fb.capacity, dtype=torch.int32, device=self.device)
                 continue
             self.ctx.check(rc)
             break
@@ -244,7 +246,8 @@ class Trainer:
             p(P["opacities"]), p(P["shs"]), p(P["scales"]), p(P["rotations"]), p(fb.radii), p(fb.xy),
             p(fb.conic_opacity), p(fb.colors), p(fb.clamped_state), p(fb.cov3Ds), p(fb.point_list), p(fb.ranges),
             p(fb.final_T), p(fb.n_contrib), p(fb.dpix), p(out["positions"]), p(fb.dL_dcolor), p(out["shs"]),
-            p(out["opacities"]), p(out["scales"]), p(out["rotations"]), p(fb.dL_dmean2D), p(fb.dL_dconic), p(None))
+            p(out["opacities"]), p(out["scales"]), p(out["rotations"]), p(fb.dL_dmean2D), p(fb.dL_dconic), p(None),
+            p(fb.block_masks))
         self.ctx.check(rc)
 
     # ---- one optimisation step -------------------------------------------------------------------

@@ -209,13 +209,14 @@ def stage_table(torch, T, cam_index, target, iters=10):
         "tile_ranges": (lambda: L.gsb_tile_ranges(ctx.h, s(), D, p(keys_s), Tg, p(fb.ranges)), 8 * D + 8 * Tg),
         "blend_forward": (lambda: L.gsb_blend_forward(ctx.h, s(), C.byref(frame), p(fb.ranges), p(fb.point_list), p(fb.xy),
                                                       p(fb.colors), p(fb.conic_opacity), p(fb.depths), p(fb.image),
-                                                      p(fb.depth), p(fb.final_T), p(fb.n_contrib)), 44 * D + 24 * Pn),
+                                                      p(fb.depth), p(fb.final_T), p(fb.n_contrib), p(fb.block_masks)), 44 * D + 24 * Pn),
         "l1_loss_grad": (lambda: L.gsb_l1_loss_grad(ctx.h, s(), 3 * Pn, p(fb.image), p(target), 1.0 / (3 * Pn), p(fb.dpix),
                                                     p(fb.loss_sum)), 36 * Pn),
         "blend_backward": (lambda: L.gsb_blend_backward(ctx.h, s(), C.byref(frame), N, p(fb.ranges), p(fb.point_list),
                                                         p(fb.xy), p(fb.conic_opacity), p(fb.colors), p(fb.final_T),
                                                         p(fb.n_contrib), p(fb.dpix), p(fb.dL_dmean2D), p(fb.dL_dconic),
-                                                        p(g["opacities"]), p(fb.dL_dcolor)), 40 * D + 20 * Pn + 44 * N),
+                                                        p(g["opacities"]), p(fb.dL_dcolor), p(fb.block_masks)),
+                           40 * D + 20 * Pn + 44 * N),
         "preprocess_backward": (lambda: L.gsb_preprocess_backward(
             ctx.h, s(), C.byref(frame), N, p(P["positions"]), p(fb.radii), p(P["shs"]), p(P["scales"]), p(P["rotations"]),
             p(fb.cov3Ds), p(fb.clamped_state), p(fb.dL_dmean2D), p(fb.dL_dconic), p(fb.dL_dcolor), p(g["positions"]),

@@ -121,11 +121,16 @@ int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s, int32_t width, int32_t height, i
                     int32_t* used_tile_path_host);
 
 /* replaces wp_render_gaussians (forward.py:384-515) and the no-op track_pixel_stats (589-627).
- * image float[H][W][3], inv_depth float[H][W], final_T float[H][W], n_contrib int32[H][W]. */
+ * image float[H][W][3], inv_depth float[H][W], final_T float[H][W], n_contrib int32[H][W].
+ * block_masks (int32, one per point_list entry; may be NULL) is an extra output with no counterpart
+ * in the reference: the per-entry culling mask the kernel computes anyway (which 8-pixel half rows
+ * of the tile the Gaussian can reach with alpha >= 1/255).  Passing it on to gsb_blend_backward
+ * saves recomputing it there; entries behind the point where a tile's pixels all terminated are
+ * not written (the backward never reads them). */
 int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, const int32_t* ranges,
                       const int32_t* point_list, const float* points_xy, const float* rgb,
                       const float* conic_opacity, const float* depths, float* image, float* inv_depth,
-                      float* final_T, int32_t* n_contrib);
+                      float* final_T, int32_t* n_contrib, int32_t* block_masks);
 
 /* The whole of render_gaussians (forward.py:629-894) in one call.  point_list has room for
  * point_list_capacity entries; *num_rendered_host receives D.  Returns GSB_ERR_CAPACITY (with D
@@ -137,17 +142,20 @@ int gsb_forward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const
                 int32_t* radii, int32_t* point_offsets, float* points_xy, float* depths, float* rgb,
                 float* cov3Ds, float* conic_opacity, float* clamped_state, int32_t* point_list,
                 int64_t point_list_capacity, int32_t* ranges, float* image, float* inv_depth, float* final_T,
-                int32_t* n_contrib, int64_t* num_rendered_host);
+                int32_t* n_contrib, int64_t* num_rendered_host, int32_t* block_masks /* optional, see above */);
 
 /* ---- backward stages -------------------------------------------------------------------- */
 
 /* replaces wp_render_backward_kernel (backward.py:558-706, launched 932-953).  Accumulates into
  * dL_dmean2D float[N][3] (z stays 0), dL_dconic float[N][4] (a, b, 0, c), dL_dopacity float[N],
- * dL_dcolor float[N][3]; the four arrays are zeroed here first (backward.py:1113-1116). */
+ * dL_dcolor float[N][3]; the four arrays are zeroed here first (backward.py:1113-1116).
+ * block_masks: the optional output of gsb_blend_forward for the SAME point_list / ranges, or NULL
+ * (the masks are then recomputed; results are identical). */
 int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const int32_t* ranges,
                        const int32_t* point_list, const float* points_xy, const float* conic_opacity,
                        const float* rgb, const float* final_T, const int32_t* n_contrib, const float* dL_dpixels,
-                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor);
+                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                       const int32_t* block_masks);
 
 /* replaces backward_preprocess (backward.py:770-888): compute_cov2d_backward_kernel,
  * compute_projection_backward_kernel, sh_backward_kernel and compute_cov3d_backward_kernel fused
@@ -168,7 +176,7 @@ int gsb_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, cons
                  const float* clamped_state, const float* cov3Ds, const int32_t* point_list, const int32_t* ranges,
                  const float* final_T, const int32_t* n_contrib, const float* dL_dpixels, float* dL_dmean3D,
                  float* dL_dcolor, float* dL_dshs, float* dL_dopacity, float* dL_dscale, float* dL_drot,
-                 float* dL_dmean2D, float* dL_dconic, float* dL_dcov3D);
+                 float* dL_dmean2D, float* dL_dconic, float* dL_dcov3D, const int32_t* block_masks /* optional */);
 
 /* ---- optimizer / densify (optimizer.py, train.py nested kernels) -------------------------- */
 

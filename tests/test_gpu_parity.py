@@ -70,7 +70,8 @@ def test_golden_from_reference_source(gs, golden_dir, name):
     g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     img, depth, buf = gs.forward.render_gaussians(**_golden_kwargs(g))
     want = {k[4:]: v for k, v in g.items() if k.startswith("fwd_")}
-    assert set(buf) == set(want)
+    # the reference's 12 keys, plus our one documented extra (the culling masks handed on to backward)
+    assert set(buf) - {"block_masks"} == set(want)
     check_forward((img, depth, buf), (g["image"], g["depth"], want), name + ": ")
     if int(g["ref_bwd_oob"]):
         return
@@ -123,13 +124,14 @@ def test_synthetic_forward_backward_vs_oracle(gs, oracle, n, w, h, smin, smax, c
         _lib.context().set_option("blend_cull", 1)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode,hand_masks_on", [(0, True), (1, True), (2, True), (0, False), (1, False)])
 @pytest.mark.parametrize("n,w,h,smin,smax,bg", [(12000, 200, 136, 0.005, 0.05, (0.0, 0.0, 0.0)),
                                                 (6000, 123, 77, 0.02, 0.3, (0.2, 0.5, 0.9))])
-def test_backward_reduction_modes_agree_with_oracle(gs, oracle, mode, n, w, h, smin, smax, bg):
+def test_backward_reduction_modes_agree_with_oracle(gs, oracle, mode, hand_masks_on, n, w, h, smin, smax, bg):
     """The three pixel reductions of the backward tile kernel (0: warp-shuffle butterfly, 1 / 2: tensor-core
     moments at 3 / 4 resident CTAs per SM) all meet the gradient tolerance, incl. ragged edge tiles,
-    Gaussians far larger than a tile and a coloured background (the bg . dL_dpixel term)."""
+    Gaussians far larger than a tile and a coloured background (the bg . dL_dpixel term) -- with the
+    forward's culling masks handed on and with the masks recomputed."""
     from gsb200 import _lib
     _lib.context().set_option("bwd_reduce", mode)
     try:
@@ -141,7 +143,11 @@ def test_backward_reduction_modes_agree_with_oracle(gs, oracle, mode, n, w, h, s
         check_forward(got, want)
         rng = np.random.default_rng(n)
         dpix = rng.normal(size=(h, w, 3)).astype(np.float32)       # arbitrary dL_dpixels, not only +-1/(3HW)
-        grads = gs.backward.backward(**gs.scene.backward_kwargs(params, cam, got[2], dpix, background=bg))
+        buffers = dict(got[2])
+        assert buffers["block_masks"].numel() == buffers["point_list"].numel()
+        if not hand_masks_on:          # the reference's 12 keys only: the backward recomputes the culling masks
+            del buffers["block_masks"]
+        grads = gs.backward.backward(**gs.scene.backward_kwargs(params, cam, buffers, dpix, background=bg))
         oracle.set_threads(1)
         ograds = oracle.backward(**gs.scene.backward_kwargs(params, cam, want[2], dpix, background=bg))
         check_grads(grads, ograds)

@@ -18,7 +18,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
 int gsb_tile_binning_max();
 int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
 int g_blend_cull = 1;
-int g_bwd_reduce = 1;
+int g_bwd_reduce = 2;
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {

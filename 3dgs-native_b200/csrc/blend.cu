@@ -97,6 +97,7 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
     if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are all finished
     const int wn = warp_compact_hits(sm.meta, cnt, my_mask, 0x7fffffff, lane, sm.widx[warp]);
     for (int q = 0; q < wn; ++q) {
+      if ((q & 3) == 0 && __all_sync(0xffffffffu, done)) break;  // every pixel of the block is finished
       const int j = wlist[q];
       const float4 a = sm.a[j];
       const float4 b = sm.b[j];

@@ -221,6 +221,15 @@ struct BwdSmem {
 // sm_100a).  x - tf32_hi(x) is exact, so hi + lo carries >= 20 mantissa bits through the MMA.
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
+// exp(x) for x <= 0 on the MUFU unit (2 ulp).  The backward's alpha only feeds tolerance-compared
+// gradients; its one decision (alpha < 1/255) can differ from the forward's for a pair within a few
+// ulp of the threshold, which changes that pixel's replayed T by 0.4% -- about one pair in 1e6.
+__device__ __forceinline__ float exp_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; x must be a normal number
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -281,8 +290,13 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
   const float dp0 = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
   const float dp1 = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
   const float dp2 = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
-  const float bgdot = gs_dot3(P.bg0, P.bg1, P.bg2, dp0, dp1, dp2);  // backward.py:679
-  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, last_alpha = 0.0f, lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;
+  // Behind-sum in scalar form.  backward.py:667-680 carries accum_rec (a colour) and evaluates
+  //   dL_dalpha_i = T_i (c_i - accum_rec_i) . dL_dpix - T_final/(1 - alpha_i) (bg . dL_dpix).
+  // With accum_rec_i T_i = (sum_{k behind i} c_k alpha_k T_k) / (1 - alpha_i) this is
+  //   dL_dalpha_i = T_i (c_i . dL_dpix) - gamma_i / (1 - alpha_i),
+  //   gamma_i = T_final (bg . dL_dpix) + sum_{k behind i} (c_k . dL_dpix) alpha_k T_k :
+  // one scalar of state instead of seven and a third of the arithmetic (same value up to rounding).
+  float gamma = T_final * gs_dot3(P.bg0, P.bg1, P.bg2, dp0, dp1, dp2);
 
   // Constant B fragments.  Logical column (kk, t) / (kk, t+4) of k-step kk is the pixel owned by
   // lane 8t + kk / 8t + 4 + kk (block coords i = kk or 4 + kk, r = t), so that a lane's A operands
@@ -359,23 +373,16 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       // the replay limit (pixel replays the entry iff position < kept), backward.py:647 (power > 0)
       // and the conservative exponent threshold
       if (__float_as_int(b.w) < kept && !(power > 0.0f) && !(power < b.z)) {
-        const float G = gs_expf(power);
+        const float G = exp_approx(power);
         const float alpha = f_min(0.99f, b.y * G);
         if (!(alpha < (1.0f / 255.0f))) {  // backward.py:655
           const float4 c = sm.c[j];
-          const float inv_1ma = rcp_approx(1.0f - alpha);      // backward.py:658,680; 1 - alpha is in [0.01, 1]
-          T = T * inv_1ma;
-          acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
-          acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
-          acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
-          lc0 = c.x;
-          lc1 = c.y;
-          lc2 = c.z;
-          float dL_dalpha = gs_dot3(c.x - acc0, c.y - acc1, c.z - acc2, dp0, dp1, dp2);
-          dL_dalpha *= T;
-          last_alpha = alpha;
-          dL_dalpha += (-T_final * inv_1ma) * bgdot;
-          wv = alpha * T;          // d(channel)/d(colour), backward.py:672
+          const float inv_1ma = rcp_approx(1.0f - alpha);     // backward.py:658,680; 1 - alpha is in [0.01, 1]
+          T = T * inv_1ma;                                   // T_i
+          wv = alpha * T;                                    // d(channel)/d(colour), backward.py:672
+          const float dc = gs_dot3(c.x, c.y, c.z, dp0, dp1, dp2);
+          const float dL_dalpha = T * dc - gamma * inv_1ma;
+          gamma = fmaf(dc, wv, gamma);
           sv = G * dL_dalpha;      // dL_dG = opacity * dL_dalpha is applied after the reduction
         }
       }

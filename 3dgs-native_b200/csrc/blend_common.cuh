@@ -20,32 +20,52 @@ struct BlendParams {
   int cull;  // 1: per-block culling masks (default); 0: keep every list entry (A/B switch, same results)
 };
 
+__device__ __forceinline__ float gs_sqrt_approx(float x) {  // MUFU.SQRT, ~1 ulp
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // 32-bit mask, bit (2*r + h): on tile row r the Gaussian can reach alpha >= 1/255 for some pixel of
-// the 8-column half h.  Solves power(x) >= thr for x on every row (a quadratic in dx) with margins
-// that dwarf the rounding errors; every comparison is written so that NaN / degenerate conics fall
-// on the "keep" side.  `thr` is gs_power_threshold(opacity).
+// the 8-column half h.  `thr` is gs_power_threshold(opacity):  power >= thr  <=>
+//   q(dx, dy) = a dx^2 + 2 b dx dy + c dy^2 <= t2 = -2 thr        (dx = gx - px, dy = gy - py).
+// On a row (dy fixed) that is  px in [xc - hw, xc + hw]  with  xc = gx + (b/a) dy  and
+// hw^2 = t2/a - (c/a - (b/a)^2) dy^2.  Everything is conservative: t2 carries the threshold's own
+// margin, hw^2 is inflated by 1e-5 of the magnitude of each of its terms (two orders above their
+// rounding errors), the interval by 0.05 px + 1e-3/a, and Gaussians whose coordinates are large
+// enough for fp32 rounding to approach that margin, or whose conic is degenerate / NaN, keep every
+// bit.  Every comparison is written so that a NaN falls on the "keep" side.  Explicit FMAs: the
+// function gives the same value in translation units built with and without -fmad.
 __device__ __forceinline__ unsigned gs_block_mask(float gx, float gy, float ca, float cb, float cc, float thr,
                                                   float x0, float y0) {
   if (thr == __int_as_float(0x7f800000)) return 0u;  // opacity < 1/255: alpha can never reach 1/255
-  const float t2 = -2.0f * thr * 1.0001f + 1e-3f;    // q = a dx^2 + 2b dx dy + c dy^2 <= t2  <=>  power >= thr
-  const float inv_a = 1.0f / ca;
+  if (!(ca > 0.0f)) return 0xffffffffu;
+  const float t2 = __fmaf_rn(-2.0f * thr, 1.0001f, 1e-3f);
+  const float inv_a = __fdiv_rn(1.0f, ca);
+  const float kb = __fmul_rn(cb, inv_a);
+  const float ck = __fmul_rn(cc, inv_a);
+  const float kb2 = __fmul_rn(kb, kb);
+  const float K0 = __fmul_rn(t2, inv_a);
+  const float K0i = __fmaf_rn(1e-5f, fabsf(K0), K0) + __fmul_rn(1e-6f * inv_a, inv_a);
+  const float K3 = __fmaf_rn(1e-5f, kb2 + fabsf(ck), kb2 - ck);   // -(c/a - (b/a)^2), inflated
+  const float m = __fmaf_rn(1e-3f, inv_a, 0.05f);
+  // magnitude guard: with every coordinate below 3e4 the fp32 / MUFU errors stay under 0.03 px
+  const float dy_max = fabsf(gy - y0) + 16.0f;
+  const float reach = fabsf(gx) + fabsf(kb) * dy_max + gs_sqrt_approx(fabsf(K0i) + fabsf(K3) * dy_max * dy_max);
+  if (!(reach < 3e4f) || !(dy_max < 3e4f)) return 0xffffffffu;
+  const float gx_lo = gx - m, gx_hi = gx + m;
+  const float xa = x0 + 7.0f, xb = x0 + 8.0f, xe = x0 + 15.0f;
   unsigned mask = 0u;
-#pragma unroll 2
+#pragma unroll 4
   for (int r = 0; r < 16; ++r) {
     const float dy = gy - (y0 + (float)r);
-    const float bd = cb * dy;
-    const float bd2 = bd * bd;
-    const float ac = ca * (cc * dy * dy - t2);
-    // discriminant of a dx^2 + 2 bd dx + (c dy^2 - t2) <= 0, inflated by 100x the worst rounding error
-    const float disc = (bd2 - ac) + 1e-5f * (bd2 + fabsf(ac)) + 1e-6f;
-    const float sq = sqrtf(fmaxf(disc, 0.0f)) + 1e-3f;
-    // dx in [(-bd - sq)/a, (-bd + sq)/a]  =>  pixel x = gx - dx
-    const float px_lo = gx - (-bd + sq) * inv_a - 0.05f;
-    const float px_hi = gx - (-bd - sq) * inv_a + 0.05f;
-    const bool conic_ok = ca > 0.0f;
-    const bool row_miss = conic_ok && (disc < 0.0f);
-    const bool miss0 = row_miss || (conic_ok && ((px_lo > x0 + 7.0f) || (px_hi < x0)));
-    const bool miss1 = row_miss || (conic_ok && ((px_lo > x0 + 15.0f) || (px_hi < x0 + 8.0f)));
+    const float h2 = __fmaf_rn(K3, __fmul_rn(dy, dy), K0i);
+    const float hw = gs_sqrt_approx(fmaxf(h2, 0.0f));
+    const float lo = __fmaf_rn(kb, dy, gx_lo) - hw;
+    const float hi = __fmaf_rn(kb, dy, gx_hi) + hw;
+    const bool row_miss = h2 < 0.0f;
+    const bool miss0 = row_miss || (lo > xa) || (hi < x0);
+    const bool miss1 = row_miss || (lo > xe) || (hi < xb);
     if (!miss0) mask |= (1u << (2 * r));
     if (!miss1) mask |= (1u << (2 * r + 1));
   }

@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--cull", type=int, default=1)
-    ap.add_argument("--bwd-reduce", type=int, default=1, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
+    ap.add_argument("--bwd-reduce", type=int, default=2, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -70,8 +70,8 @@ int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered);
 int64_t gsb_launch_count(gsb_ctx* ctx);
 /* tuning / A-B knobs outside the reference surface (process-wide; results never depend on them):
  *   "blend_cull" = 1 (default) / 0: per-block culling masks in the tile kernels
- *   "bwd_reduce" = 1 (default) / 2: the backward tile kernel sums the per-pixel terms over a warp's
- *                  pixel block with TF32 tensor-core products (3 / 4 resident CTAs per SM);
+ *   "bwd_reduce" = 2 (default) / 1: the backward tile kernel sums the per-pixel terms over a warp's
+ *                  pixel block with TF32 tensor-core products (4 / 3 resident CTAs per SM);
  *                  0: warp-shuffle butterfly
  *   "binning"    = 0 (default): gsb_forward bins by tile with a counting sort and sorts every tile's
  *                  segment in shared memory; 1: duplicate-with-keys + global 64-bit radix sort */

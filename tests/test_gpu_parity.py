@@ -153,7 +153,7 @@ def test_backward_reduction_modes_agree_with_oracle(gs, oracle, mode, hand_masks
         check_grads(grads, ograds)
     finally:
         oracle.set_threads(1)
-        _lib.context().set_option("bwd_reduce", 1)
+        _lib.context().set_option("bwd_reduce", 2)
 
 
 def test_nothing_visible_gives_zero_image(gs, oracle):

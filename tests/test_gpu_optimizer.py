@@ -185,3 +185,42 @@ def test_checkpoint_resume(gs, tmp_path):
     assert torch.equal(T2.adam_m.flat, T.adam_m.flat) and torch.equal(T2.adam_v.flat, T.adam_v.flat)
     T2.train_step(nxt, [3], densify=False)
     assert torch.isfinite(T2.params.flat).all()
+
+
+def test_adam_division_is_bit_identical_to_the_operator(gs):
+    """The Adam kernels divide through gs_div_pos (exponent set aside, fast-path sequence, exponent put
+    back).  It must equal `a / b` bit for bit: numerators over the whole binary32 range incl. zeros,
+    subnormals, huge values, inf and NaN; divisors like Adam's (bias corrections, sqrt(v)+eps) and
+    outside the fast window."""
+    import ctypes as C
+    from gsb200 import _lib
+    ctx = _lib.context()
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    bits = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)       # every exponent, both signs
+    a = bits.view(np.float32).copy()
+    a[:64] = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1.17549435e-38, 3e38, -3e38] + [1e-30] * 54,
+                      dtype=np.float32)
+    b = np.empty(n, dtype=np.float32)
+    q = n // 4
+    b[:q] = (1.0 - 0.9 ** rng.integers(1, 400, q)).astype(np.float32)            # bc1
+    b[q:2 * q] = (1.0 - 0.999 ** rng.integers(1, 7000, q)).astype(np.float32)    # bc2
+    b[2 * q:3 * q] = np.exp(rng.uniform(np.log(1e-9), np.log(1e3), q)).astype(np.float32)   # sqrt(v^) + eps
+    b[3 * q:] = np.exp(rng.uniform(np.log(1e-30), np.log(1e30), n - 3 * q)).astype(np.float32)  # outside the window too
+    b[-8:] = np.array([1.0, 0.99999994, 1.0000001, 2.0 ** -40, 2.0 ** 40, 2.0 ** -41, 1e-45, np.inf], dtype=np.float32)
+    # small numerators against each divisor class as well (the case Adam is in all the time)
+    a[1::3] = (a[1::3] * np.float32(1e-20)).astype(np.float32)
+    ta, tb = _cuda(a), _cuda(b)
+    fast, ref = torch.empty_like(ta), torch.empty_like(ta)
+    ctx.check(_lib.lib().gsb_selftest_div(ctx.h, _lib.stream_ptr(ctx.device_index), n, _lib.ptr(ta), _lib.ptr(tb),
+                                          _lib.ptr(fast), _lib.ptr(ref)))
+    torch.cuda.synchronize()
+    f, r = fast.cpu().numpy().view(np.uint32), ref.cpu().numpy().view(np.uint32)
+    both_nan = np.isnan(fast.cpu().numpy()) & np.isnan(ref.cpu().numpy())
+    bad = (f != r) & ~both_nan
+    assert not bad.any(), f"{bad.sum()} of {n} quotients differ, e.g. a={a[bad][:3]} b={b[bad][:3]}"
+    # and against the host's IEEE division
+    with np.errstate(all="ignore"):
+        host = (a / b).view(np.uint32)
+    ok = (host == f) | both_nan
+    assert ok.all(), f"{(~ok).sum()} quotients differ from the host division"

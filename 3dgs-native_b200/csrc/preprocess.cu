@@ -26,24 +26,41 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
   const int tid = threadIdx.x;
   const int rows = min(kPreThreads, n - base);
 
-  // cooperative, coalesced SH load (12 float4 per Gaussian)
+  // This thread's own inputs first, so that they are in flight together with the SH tile (the loads
+  // below are independent; issued after the barrier they would cost a second DRAM round trip).
+  const int i = base + tid;
+  const bool live = i < n;
+  const int il = live ? i : base;  // clamped: dead threads of the last CTA re-read row 0 and store nothing
+  const float px = means[3 * il + 0], py = means[3 * il + 1], pz = means[3 * il + 2];
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + il);  // (x,y,z,w)
+  const float sc0 = scales[3 * il + 0], sc1 = scales[3 * il + 1], sc2 = scales[3 * il + 2];
+  const float opacity = __ldg(opac + il);
+
+  // cooperative, coalesced SH load (12 float4 per Gaussian), all twelve in flight
   {
     const float4* src = reinterpret_cast<const float4*>(shs + (size_t)base * 48);
     const int chunks = rows * 12;
-#pragma unroll 4
-    for (int c = tid; c < chunks; c += kPreThreads) {
-      float4 v = __ldg(src + c);
-      int g = c / 12, q = c - g * 12;
-      float* d = s_sh + g * kShStride + q * 4;
-      d[0] = v.x;
-      d[1] = v.y;
-      d[2] = v.z;
-      d[3] = v.w;
+    float4 v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = tid + k * kPreThreads;
+      v[k] = (c < chunks) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = tid + k * kPreThreads;
+      if (c < chunks) {
+        const int g = c / 12, qd = c - g * 12;
+        float* d = s_sh + g * kShStride + qd * 4;
+        d[0] = v[k].x;
+        d[1] = v[k].y;
+        d[2] = v[k].z;
+        d[3] = v[k].w;
+      }
     }
   }
   __syncthreads();
-  const int i = base + tid;
-  if (i >= n) return;
+  if (!live) return;
 
   // outputs default to zero: forward.py:703-710 allocates them with wp.zeros
   int o_radius = 0, o_tiles = 0;
@@ -53,7 +70,6 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
   float o_cl[3] = {0.f, 0.f, 0.f};
   float4 o_con = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const float px = means[3 * i + 0], py = means[3 * i + 1], pz = means[3 * i + 2];
   do {
     float p_view[4];
     gs_vec4_mul_mat44(px, py, pz, 1.0f, f.view, p_view);
@@ -67,10 +83,9 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     // ---- compute_cov3d, forward.py:146-186 ([Warp] quat_to_matrix via quat_rotate) ----
     float cov3d[6];
     {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + i);  // (x,y,z,w)
-      const float s0 = f.scale_modifier * scales[3 * i + 0];
-      const float s1 = f.scale_modifier * scales[3 * i + 1];
-      const float s2 = f.scale_modifier * scales[3 * i + 2];
+      const float s0 = f.scale_modifier * sc0;
+      const float s1 = f.scale_modifier * sc1;
+      const float s2 = f.scale_modifier * sc2;
       float R[9];
       float c = 2.0f * q.w * q.w - 1.0f;
       float d;
@@ -192,7 +207,7 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     o_radius = f2i(my_radius);
     o_x = pix;
     o_y = piy;
-    o_con = make_float4(conic0, conic1, conic2, __ldg(opac + i));
+    o_con = make_float4(conic0, conic1, conic2, opacity);
     o_tiles = (rmaxy - rminy) * (rmaxx - rminx);
   } while (false);
 

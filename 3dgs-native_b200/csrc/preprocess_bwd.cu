@@ -20,7 +20,7 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kShStride = 49;
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict__ means, const int* __restrict__ radii,
                            const float* __restrict__ shs, const float* __restrict__ scales,
                            const float* __restrict__ rots, const float* __restrict__ cov3Ds,
@@ -32,23 +32,45 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
   const int base = blockIdx.x * kThreads;
   const int tid = threadIdx.x;
   const int rows = min(kThreads, n - base);
+  // This thread's own inputs first: they are independent of the SH tile and would otherwise cost a
+  // second DRAM round trip after the barrier.
+  const int i = base + tid;
+  const int il = (i < n) ? i : base;  // clamped: the dead threads of the last CTA re-read row 0
+  const int in_radius = radii[il];
+  const float mx = means[3 * il + 0], my = means[3 * il + 1], mz = means[3 * il + 2];
+  const float2 c3a = *reinterpret_cast<const float2*>(cov3Ds + (size_t)il * 6);
+  const float2 c3b = *reinterpret_cast<const float2*>(cov3Ds + (size_t)il * 6 + 2);
+  const float2 c3c = *reinterpret_cast<const float2*>(cov3Ds + (size_t)il * 6 + 4);
+  const float4 in_dcon = __ldg(reinterpret_cast<const float4*>(dL_dconic) + il);
+  const float in_g0 = dL_dmean2D[3 * il + 0], in_g1 = dL_dmean2D[3 * il + 1];
+  const float in_dcol[3] = {dL_dcolor[3 * il + 0], dL_dcolor[3 * il + 1], dL_dcolor[3 * il + 2]};
+  const float in_cl[3] = {clamped_state[3 * il + 0], clamped_state[3 * il + 1], clamped_state[3 * il + 2]};
+  const float4 in_q = __ldg(reinterpret_cast<const float4*>(rots) + il);
+  const float in_s0 = scales[3 * il + 0], in_s1 = scales[3 * il + 1], in_s2 = scales[3 * il + 2];
   {
     const float4* src = reinterpret_cast<const float4*>(shs + (size_t)base * 48);
     const int chunks = rows * 12;
-#pragma unroll 4
-    for (int c = tid; c < chunks; c += kThreads) {
-      float4 v = __ldg(src + c);
-      int g = c / 12, q = c - g * 12;
-      float* d = s_sh + g * kShStride + q * 4;
-      d[0] = v.x;
-      d[1] = v.y;
-      d[2] = v.z;
-      d[3] = v.w;
+    float4 v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = tid + k * kThreads;
+      v[k] = (c < chunks) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = tid + k * kThreads;
+      if (c < chunks) {
+        const int g = c / 12, q = c - g * 12;
+        float* d = s_sh + g * kShStride + q * 4;
+        d[0] = v[k].x;
+        d[1] = v[k].y;
+        d[2] = v[k].z;
+        d[3] = v[k].w;
+      }
     }
   }
   __syncthreads();
 
-  const int i = base + tid;
   float* sh = s_sh + tid * kShStride;  // this thread's row: SH in, dL_dSH out
   if (i < n) {
     float o_mean[3] = {0.f, 0.f, 0.f};
@@ -57,12 +79,11 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
     float o_dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool sh_written = false;
 
-    if (radii[i] > 0) {
-      const float mx = means[3 * i + 0], my = means[3 * i + 1], mz = means[3 * i + 2];
+    if (in_radius > 0) {
       // ================= compute_cov2d_backward_kernel, backward.py:258-435 =================
       {
-        const float* c3 = cov3Ds + (size_t)i * 6;
-        const float dcon0 = dL_dconic[4 * i + 0], dcon1 = dL_dconic[4 * i + 1], dcon2 = dL_dconic[4 * i + 3];
+        const float c3[6] = {c3a.x, c3a.y, c3b.x, c3b.y, c3c.x, c3c.y};
+        const float dcon0 = in_dcon.x, dcon1 = in_dcon.y, dcon2 = in_dcon.w;
         float t[4];
         gs_vec4_mul_mat44(mx, my, mz, 1.0f, f.view, t);
         const float limx = 1.3f * f.tan_fovx;
@@ -152,7 +173,7 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
       }
       // ================= compute_projection_backward_kernel, backward.py:708-768 =================
       {
-        const float g0 = dL_dmean2D[3 * i + 0], g1 = dL_dmean2D[3 * i + 1];
+        const float g0 = in_g0, g1 = in_g1;
         float m_hom[4];
         gs_vec4_mul_mat44(mx, my, mz, 1.0f, f.proj, m_hom);
         const float m_w = 1.0f / (m_hom[3] + 0.0000001f);
@@ -176,7 +197,7 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
           float dRGB[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c)  // mask applied regardless of the forward `clamped` flag
-            dRGB[c] = dL_dcolor[3 * i + c] * (1.0f + (-1.0f * clamped_state[3 * i + c]));
+            dRGB[c] = in_dcol[c] * (1.0f + (-1.0f * in_cl[c]));
           float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
           float basis[16];
 #pragma unroll
@@ -262,14 +283,13 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
       }
       // ================= compute_cov3d_backward_kernel, backward.py:438-556 (G2, G3) =================
       {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + i);
+        const float4 q = in_q;
         const float r = q.w, x = q.x, y = q.y, z = q.z;
         const float R[9] = {1.0f - 2.0f * (y * y + z * z), 2.0f * (x * y - r * z),        2.0f * (x * z + r * y),
                             2.0f * (x * y + r * z),        1.0f - 2.0f * (x * x + z * z), 2.0f * (y * z - r * x),
                             2.0f * (x * z - r * y),        2.0f * (y * z + r * x),        1.0f - 2.0f * (x * x + y * y)};
         const float scale_modifier = 1.0f;  // quirk G3: backward() never forwards the caller's value
-        const float sv0 = scale_modifier * scales[3 * i + 0], sv1 = scale_modifier * scales[3 * i + 1],
-                    sv2 = scale_modifier * scales[3 * i + 2];
+        const float sv0 = scale_modifier * in_s0, sv1 = scale_modifier * in_s1, sv2 = scale_modifier * in_s2;
         const float S[9] = {sv0, 0.f, 0.f, 0.f, sv1, 0.f, 0.f, 0.f, sv2};
         float M[9];
         gs_mat33_mul(S, R, M);
@@ -345,6 +365,8 @@ GSB_API int gsb_preprocess_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame*
   if (n == 0) return GSB_OK;
   GSB_REQUIRE(ctx, gsb_aligned16(shs) && gsb_aligned16(dL_dshs) && gsb_aligned16(rotations) && gsb_aligned16(dL_drot),
               "gsb_preprocess_backward: shs, dL_dshs, rotations, dL_drot must be 16-byte aligned");
+  GSB_REQUIRE(ctx, gsb_aligned16(dL_dconic) && (reinterpret_cast<uintptr_t>(cov3Ds) & 7u) == 0,
+              "gsb_preprocess_backward: dL_dconic must be 16-byte and cov3Ds 8-byte aligned");
   GSB_REQUIRE(ctx, !dL_dcov3D_internal || (reinterpret_cast<uintptr_t>(dL_dcov3D_internal) & 7u) == 0,
               "gsb_preprocess_backward: dL_dcov3D_internal must be 8-byte aligned");
   FrameK k;

@@ -12,9 +12,13 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
 int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
                            const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
                            int64_t* num_rendered_host, int* max_count_host);
+int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles);
+int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges);
+int gsb_tile_binning_wait(gsb_ctx* ctx, int64_t* num_rendered_host, int* max_count_host);
 int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                          const float* depths, const int32_t* radii, const int32_t* point_offsets,
-                          const int32_t* ranges, int64_t num_rendered, int max_count, int32_t* point_list);
+                          const float* depths, const int32_t* radii, const int32_t* rank_index,
+                          int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
+                          int32_t* point_list);
 int gsb_tile_binning_max();
 int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
 int g_blend_cull = 1;
@@ -72,11 +76,13 @@ int gsb_reserve_binning(gsb_ctx* ctx, cudaStream_t s, int64_t num_rendered) {
 
 static int reserve_per_gaussian(gsb_ctx* ctx, cudaStream_t s, int64_t n) {
   if (n <= ctx->n_cap) return GSB_OK;
-  int64_t c0 = ctx->n_cap, c1 = ctx->n_cap;
+  int64_t c0 = ctx->n_cap, c1 = ctx->n_cap, c2 = ctx->n_cap;
   int rc;
   if ((rc = gsb_grow(ctx, (void**)&ctx->tiles_touched, &c0, n, sizeof(int32_t), s)) != GSB_OK) return rc;
   if ((rc = gsb_grow(ctx, (void**)&ctx->dcov3d, &c1, n * 6, sizeof(float), s)) != GSB_OK) return rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->rank_base, &c2, n, sizeof(int32_t), s)) != GSB_OK) return rc;
   ctx->n_cap = c0 < c1 / 6 ? c0 : c1 / 6;
+  ctx->n_cap = ctx->n_cap < c2 ? ctx->n_cap : c2;
   return GSB_OK;
 }
 
@@ -101,7 +107,8 @@ GSB_API int gsb_create(gsb_ctx** out, int device) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
   if (cudaMalloc((void**)&ctx->d_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
-      cudaMalloc((void**)&ctx->sort_small, (256 + 16) * sizeof(uint32_t)) != cudaSuccess) {
+      cudaMalloc((void**)&ctx->sort_small, (256 + 16) * sizeof(uint32_t)) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_count, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return GSB_ERR_NOMEM;
   }
@@ -121,6 +128,8 @@ GSB_API int gsb_destroy(gsb_ctx* ctx) {
   for (void* p : bufs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+  if (ctx->rank_base) cudaFree(ctx->rank_base);
+  if (ctx->ev_count) cudaEventDestroy(ctx->ev_count);
   delete ctx;
   return GSB_OK;
 }
@@ -189,7 +198,7 @@ GSB_API int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s_, int32_t width, int32_t 
   if (D == 0) return GSB_OK;  // ranges are all (0,0) already
   if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
     // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
-    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, point_offsets, ranges, D,
+    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, point_offsets, 0, ranges, D,
                                max_count, point_list);
     if (rc != GSB_OK) return rc;
     if (used_tile_path_host) *used_tile_path_host = 1;
@@ -226,19 +235,49 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   int rc;
   if ((rc = reserve_per_gaussian(ctx, s, n)) != GSB_OK) return rc;
 
-  // forward.py:719-752
-  rc = gsb_preprocess(ctx, s_, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds, rgb,
-                      conic_opacity, ctx->tiles_touched, clamped_state);
-  if (rc != GSB_OK) return rc;
-  // forward.py:755-764: inclusive scan (an output of the operator).  The one host read-back of the
-  // frame (num_rendered, and the longest tile list) comes from the per-tile counting pass below.
-  rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr);
-  if (rc != GSB_OK) return rc;
+  // forward.py:719-788.  Preprocess also runs the counting pass of the tile binning; the per-tile
+  // scan and the read-back of D (the frame's one host wait) follow at once, and the inclusive scan of
+  // tiles_touched -- an output of the operator, not an input of this binning -- is queued BEHIND the
+  // read-back so that it runs while the host wakes up and launches the rest.
   int64_t D = 0;
-  rc = gsb_bin_by_tile(ctx, s_, f->width, f->height, n, points_xy, depths, radii, point_offsets, point_list,
-                       point_list_capacity, ranges, &D, nullptr);
+  int max_count = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if ((rc = gsb_tile_binning_prepare(ctx, s, n, num_tiles)) != GSB_OK) return rc;
+    PreBin bin{ctx->tile_count, ctx->vals_a, ctx->rank_base, ctx->d_scalars + 8, (long long)ctx->bin_cap};
+    rc = gsb_preprocess_impl(ctx, s, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds,
+                             rgb, conic_opacity, ctx->tiles_touched, clamped_state, &bin);
+    if (rc != GSB_OK) return rc;
+    if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges)) != GSB_OK) return rc;
+    // forward.py:755-764: inclusive scan
+    if ((rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK) return rc;
+    if ((rc = gsb_tile_binning_wait(ctx, &D, &max_count)) != GSB_OK) return rc;
+    if (D <= ctx->bin_cap || D > GSB_MAX_RENDERED) break;
+    // first frame / scene grew: the rank buffer was too small.  Grow it and redo the pass.
+    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+  }
   if (num_rendered_host) *num_rendered_host = D;
-  if (rc != GSB_OK) return rc;
+  if (D > (1LL << 30))  // forward.py:765-767
+    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "Number of rendered points exceeds the maximum supported by Warp.");
+  if (D > GSB_MAX_RENDERED)
+    return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "num_rendered == 2^30 is not supported by the radix sort (max 2^30-1)");
+  if (D > point_list_capacity)
+    return gsb_set_error(ctx, GSB_ERR_CAPACITY, "point_list capacity %lld < num_rendered %lld",
+                         (long long)point_list_capacity, (long long)D);
+  if (D > 0) {
+    if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
+      // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
+      rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ctx->rank_base, 1, ranges, D,
+                                 max_count, point_list);
+      if (rc != GSB_OK) return rc;
+    } else {
+      // a tile list too long for the shared-memory sort (or the A/B switch): the reference's own
+      // sequence on the global radix sort; it rewrites ranges
+      int64_t D2 = 0;
+      rc = gsb_bin_by_tile(ctx, s_, f->width, f->height, n, points_xy, depths, radii, point_offsets, point_list,
+                           point_list_capacity, ranges, &D2, nullptr);
+      if (rc != GSB_OK) return rc;
+    }
+  }
   if (D == 0) {
     // forward.py:830: nothing is launched; every image-shaped output keeps its wp.zeros() state
     // (ranges were already written as all (0,0) by the counting pass)

@@ -30,16 +30,20 @@
 
 namespace {
 
+#ifndef GSB_FWD_MINB
+#define GSB_FWD_MINB 5
+#endif
+
 struct FwdSmem {
-  float4 a[256];   // x, y, conic.a, conic.b
-  float4 b[256];   // conic.c, opacity, power threshold, 1/depth
+  float4 a[256];   // x, y, conic.a, conic.c   (two packed pairs: see gs_power_packed)
+  float4 b[256];   // conic.b, opacity, power threshold, 1/depth
   float4 c[256];   // r, g, b, 1-based position in the tile's list (int bits)
   int2 meta[256];  // 1-based position, block mask (read by the per-warp compaction)
   int wcnt[8];
   unsigned char widx[8][256];  // per warp: the staged entries that touch its block
 };
 
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, GSB_FWD_MINB)
 blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
                      const float2* __restrict__ xy, const float* __restrict__ rgb,
                      const float4* __restrict__ conic_opacity, const float* __restrict__ depths,
@@ -56,14 +60,14 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
   const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
   // A finished pixel (outside the image, or T ran out) gets a NaN x coordinate: its exponent is
   // then NaN and fails the range test below, so the inner loop needs no separate `done` test.
-  float pxf = (float)px;
+  const float pxf = (float)px;
   const float pyf = (float)py;
   const unsigned my_mask = gs_warp_mask(warp);
   const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
   const bool inside = (px < P.W && py < P.H);
 
   bool done = !inside;
-  if (done) pxf = __int_as_float(0x7fc00000);
+  gs_f2 npxy = gs_pack2(done ? __int_as_float(0x7fc00000) : -pxf, -pyf);  // (-px, -py), NaN once finished
   float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dp = 0.0f;
   int last = 0;
 
@@ -81,8 +85,8 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
       const float thr = gs_power_threshold(co.w);
       bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
       if (block_masks) block_masks[range.x + base + tid] = bmask;  // handed on to the backward
-      ea = make_float4(p.x, p.y, co.x, co.y);
-      eb = make_float4(co.z, co.w, thr, 1.0f / depths[gid]);
+      ea = make_float4(p.x, p.y, co.x, co.z);
+      eb = make_float4(co.y, co.w, thr, 1.0f / depths[gid]);
       ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(base + tid + 1));
     }
     int cnt;
@@ -96,35 +100,55 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
     __syncthreads();
     if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are all finished
     const int wn = warp_compact_hits(sm.meta, cnt, my_mask, 0x7fffffff, lane, sm.widx[warp]);
-    for (int q = 0; q < wn; ++q) {
-      if ((q & 3) == 0 && __all_sync(0xffffffffu, done)) break;  // every pixel of the block is finished
-      const int j = wlist[q];
-      const float4 a = sm.a[j];
-      const float4 b = sm.b[j];
-      const float dx = a.x - pxf;
-      const float dy = a.y - pyf;
-      const float power = gs_power(a.z, a.w, b.x, dx, dy);
-      // forward.py:474 skips power > 0; power < b.z is provably alpha < 1/255 (gs_power_threshold);
-      // written so that the NaN of a finished pixel is skipped too
-      if (!(power <= 0.0f) || !(power >= b.z)) continue;
-      const float alpha = f_min(0.99f, b.y * gs_expf(power));
-      if (alpha < (1.0f / 255.0f)) continue;
+    // One hit: alpha is known and >= 1/255.  forward.py:483-499.
+    auto blend_hit = [&](const float alpha, const int j, const float inv_z) {
       const float test_T = T * (1.0f - alpha);
       if (test_T < 0.0001f) {            // forward.py:487: the breaking Gaussian is not counted
         done = true;
-        pxf = __int_as_float(0x7fc00000);
-        continue;
+        npxy = gs_pack2(__int_as_float(0x7fc00000), -pyf);
+        return;
       }
       // Colour / depth sums are tolerance-compared (1e-4): one product alpha*T and an FMA per
-      // channel.  T, alpha and every decision above keep the exact operation order of the contract.
+      // channel.  T, alpha and every decision keep the exact operation order of the contract.
       const float4 c = sm.c[j];
       const float w = alpha * T;
       C0 = __fmaf_rn(c.x, w, C0);
       C1 = __fmaf_rn(c.y, w, C1);
       C2 = __fmaf_rn(c.z, w, C2);
-      Dp = __fmaf_rn(b.w, w, Dp);
+      Dp = __fmaf_rn(inv_z, w, Dp);
       T = test_T;
       last = __float_as_int(c.w);
+    };
+    // Two hits per iteration: their exponents and exponentials are independent, so they share the
+    // packed FFMA2 sequence; only the T recurrence is sequential.
+    int q = 0;
+    for (; q + 1 < wn; q += 2) {
+      if ((q & 3) == 0 && __all_sync(0xffffffffu, done)) break;  // every pixel of the block is finished
+      const int jA = wlist[q], jB = wlist[q + 1];
+      const float4 aA = sm.a[jA], bA = sm.b[jA];
+      const float4 aB = sm.a[jB], bB = sm.b[jB];
+      const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);
+      const float pwB = gs_power_packed(gs_pack2(aB.x, aB.y), npxy, gs_pack2(aB.z, aB.w), bB.x);
+      // forward.py:474 skips power > 0; power < thr is provably alpha < 1/255 (gs_power_threshold);
+      // written so that the NaN of a finished pixel is skipped too
+      const bool okA = (pwA <= 0.0f) && (pwA >= bA.z);
+      const bool okB = (pwB <= 0.0f) && (pwB >= bB.z);
+      if (!(okA || okB)) continue;
+      float GA, GB;
+      gs_expf2(pwA, pwB, GA, GB);
+      const float alphaA = f_min(0.99f, bA.y * GA);
+      const float alphaB = f_min(0.99f, bB.y * GB);
+      if (okA && !(alphaA < (1.0f / 255.0f))) blend_hit(alphaA, jA, bA.w);
+      if (okB && !done && !(alphaB < (1.0f / 255.0f))) blend_hit(alphaB, jB, bB.w);
+    }
+    if (q < wn) {  // odd tail
+      const int j = wlist[q];
+      const float4 a = sm.a[j], b4 = sm.b[j];
+      const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
+      if ((power <= 0.0f) && (power >= b4.z)) {
+        const float alpha = f_min(0.99f, b4.y * gs_expf(power));
+        if (!(alpha < (1.0f / 255.0f))) blend_hit(alpha, j, b4.w);
+      }
     }
   }
 

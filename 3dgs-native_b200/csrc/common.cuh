@@ -43,7 +43,9 @@ struct gsb_ctx {
   // per-Gaussian internal buffers for gsb_forward / gsb_backward
   int32_t* tiles_touched = nullptr;
   float* dcov3d = nullptr;
+  int32_t* rank_base = nullptr;  // index of a Gaussian's first arrival rank (fused counting pass)
   int64_t n_cap = 0;
+  cudaEvent_t ev_count = nullptr;  // recorded behind the read-back of D: the host waits on it, not on the stream
   // device + pinned host scalars
   int32_t* d_scalars = nullptr;  // [16]
   int32_t* h_scalars = nullptr;  // pinned [16]
@@ -114,6 +116,69 @@ __device__ __forceinline__ float gs_power(float ca, float cb, float cc, float dx
   float q = __fmul_rn(-0.5f, __fadd_rn(t0, t1));
   float t2 = __fmul_rn(__fmul_rn(cb, dx), dy);
   return __fsub_rn(q, t2);
+}
+
+// ---- packed binary32 pairs (FFMA2, sm_100) -----------------------------------------------------
+// Blackwell issues one FFMA2 for two independent fused multiply-adds on 64-bit register pairs.  The
+// tile kernels are instruction-issue bound, so arithmetic that comes in pairs is packed.  ptxas
+// contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even at -fmad=false, so products and sums are
+// written as FMAs themselves: a*b + (-0) and a*1 + b are exactly RN(a*b) and RN(a+b) (signed zeros
+// included), and an FMA cannot be contracted further.  Every lane rounds as the scalar code does.
+typedef unsigned long long gs_f2;
+__device__ __forceinline__ gs_f2 gs_pack2(float lo, float hi) {
+  gs_f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void gs_unpack2(gs_f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ gs_f2 gs_fma2(gs_f2 a, gs_f2 b, gs_f2 c) {
+  gs_f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ gs_f2 gs_mul2(gs_f2 a, gs_f2 b) { return gs_fma2(a, b, gs_pack2(-0.0f, -0.0f)); }
+__device__ __forceinline__ gs_f2 gs_add2(gs_f2 a, gs_f2 b) { return gs_fma2(a, gs_pack2(1.0f, 1.0f), b); }
+__device__ __forceinline__ gs_f2 gs_splat2(float c) { return gs_pack2(c, c); }
+
+// gs_power with the x / y halves packed: gxy = (gx, gy), npxy = (-px, -py), cac = (conic.a, conic.c).
+// Same operations in the same order as gs_power => the same bits.
+__device__ __forceinline__ float gs_power_packed(gs_f2 gxy, gs_f2 npxy, gs_f2 cac, float cb) {
+  const gs_f2 d = gs_add2(gxy, npxy);            // (dx, dy)
+  const gs_f2 t = gs_mul2(gs_mul2(cac, d), d);   // ((a*dx)*dx, (c*dy)*dy)
+  float dx, dy, t0, t1;
+  gs_unpack2(d, dx, dy);
+  gs_unpack2(t, t0, t1);
+  const float q = __fmul_rn(-0.5f, __fadd_rn(t0, t1));
+  const float t2 = __fmul_rn(__fmul_rn(cb, dx), dy);
+  return __fsub_rn(q, t2);
+}
+
+// gs_expf of two arguments at once (lo, hi): the same operation sequence per half => the same bits.
+__device__ __forceinline__ void gs_expf2(float x0, float x1, float& y0, float& y1) {
+  const gs_f2 x = gs_pack2(x0, x1);
+  const gs_f2 t = gs_mul2(x, gs_splat2(1.44269504088896341f));
+  const gs_f2 n = gs_add2(gs_add2(t, gs_splat2(12582912.0f)), gs_splat2(-12582912.0f));
+  gs_f2 r = gs_fma2(n, gs_splat2(-0.693145751953125f), x);
+  r = gs_fma2(n, gs_splat2(-1.42860682030941723212e-6f), r);
+  gs_f2 p = gs_splat2(1.9875691500e-4f);
+  p = gs_fma2(p, r, gs_splat2(1.3981999507e-3f));
+  p = gs_fma2(p, r, gs_splat2(8.3334519073e-3f));
+  p = gs_fma2(p, r, gs_splat2(4.1665795894e-2f));
+  p = gs_fma2(p, r, gs_splat2(1.6666665459e-1f));
+  p = gs_fma2(p, r, gs_splat2(5.0000001201e-1f));
+  const gs_f2 r2 = gs_mul2(r, r);
+  gs_f2 y = gs_fma2(p, r2, r);
+  y = gs_add2(y, gs_splat2(1.0f));
+  float n0, n1;
+  gs_unpack2(n, n0, n1);
+  const float s0 = __int_as_float((__float2int_rz(n0) + 127) << 23);
+  const float s1 = __int_as_float((__float2int_rz(n1) + 127) << 23);
+  y = gs_mul2(y, gs_pack2(s0, s1));
+  gs_unpack2(y, y0, y1);
+  if (x0 < -87.0f) y0 = 0.0f;
+  if (x1 < -87.0f) y1 = 0.0f;
 }
 
 // Conservative skip threshold on `power` for one Gaussian: power < thr  ==>  alpha < 1/255
@@ -202,6 +267,20 @@ struct FrameK {
 
 struct FrameK;
 void gsb_make_framek(const gsb_frame* f, FrameK* k);
+
+// Counting pass of the tile binning fused into preprocess (gsb_forward only): per-tile counters, the
+// arrival ranks, each Gaussian's first rank index and the cursor those indices are drawn from.
+struct PreBin {
+  int32_t* tile_count;
+  int32_t* rank;
+  int32_t* rank_base;
+  int32_t* cursor;
+  long long capacity;  // entries of `rank`
+};
+int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
+                        const float* scales, const float* rotations, const float* opacities, const float* shs,
+                        int32_t* radii, float* points_xy, float* depths, float* cov3Ds, float* rgb,
+                        float* conic_opacity, int32_t* tiles_touched, float* clamped_state, const PreBin* bin);
 
 // ---- stage launchers implemented across the .cu files (host side) --------------------------
 int gsb_scan_i32(gsb_ctx* ctx, cudaStream_t s, int64_t n, const int32_t* in, int32_t* out, bool exclusive,

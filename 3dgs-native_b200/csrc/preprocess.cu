@@ -15,13 +15,23 @@ namespace {
 constexpr int kPreThreads = 128;
 constexpr int kShStride = 49;
 
+constexpr int kCntStride = 32;  // ints between two tiles' counters (tilesort.cu: one 128-byte line each)
+
+// BIN = true (gsb_forward): the kernel also runs the counting pass of the tile binning -- one
+// returning atomic per (Gaussian, tile) on the tile's counter, the arrival rank stored for the
+// scatter pass -- instead of a second kernel that re-derives every rectangle.  The rank slots of
+// a CTA's Gaussians are drawn from a global cursor (one atomic per CTA), so the pass needs no prefix
+// sum of tiles_touched; that scan (an output of the operator) runs off the critical path.
+template <bool BIN>
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, const float* __restrict__ scales,
                   const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
                   int* __restrict__ radii, float2* __restrict__ xy_out, float* __restrict__ depths,
                   float* __restrict__ cov3Ds, float* __restrict__ rgb, float4* __restrict__ conic_opacity,
-                  int* __restrict__ tiles_touched, float* __restrict__ clamped_state) {
+                  int* __restrict__ tiles_touched, float* __restrict__ clamped_state, const PreBin bin) {
   __shared__ float s_sh[kPreThreads * kShStride];
+  __shared__ int s_wsum[kPreThreads / 32];
+  __shared__ int s_cta_base;
   const int base = blockIdx.x * kPreThreads;
   const int tid = threadIdx.x;
   const int rows = min(kPreThreads, n - base);
@@ -60,7 +70,7 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     }
   }
   __syncthreads();
-  if (!live) return;
+  if (!BIN && !live) return;
 
   // outputs default to zero: forward.py:703-710 allocates them with wp.zeros
   int o_radius = 0, o_tiles = 0;
@@ -69,8 +79,10 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
   float o_rgb[3] = {0.f, 0.f, 0.f};
   float o_cl[3] = {0.f, 0.f, 0.f};
   float4 o_con = make_float4(0.f, 0.f, 0.f, 0.f);
+  int rminx = 0, rminy = 0, rmaxx = 0, rmaxy = 0;
 
   do {
+    if (BIN && !live) break;
     float p_view[4];
     gs_vec4_mul_mat44(px, py, pz, 1.0f, f.view, p_view);
     if (p_view[2] < 0.2f) break;  // forward.py:250
@@ -155,7 +167,6 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     float pix = ((p_proj_x + 1.0f) * (float)f.W - 1.0f) * 0.5f;  // ndc2pix, forward.py:59-61
     float piy = ((p_proj_y + 1.0f) * (float)f.H - 1.0f) * 0.5f;
 
-    int rminx, rminy, rmaxx, rmaxy;
     gs_get_rect(pix, piy, my_radius, (float)f.grid_x, (float)f.grid_y, rminx, rminy, rmaxx, rmaxy);
     if ((rmaxx - rminx) * (rmaxy - rminy) == 0) break;  // forward.py:301
 
@@ -211,6 +222,50 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     o_tiles = (rmaxy - rminy) * (rmaxx - rminx);
   } while (false);
 
+  if (BIN) {
+    // exclusive scan of o_tiles over the CTA, one cursor atomic per CTA
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = o_tiles;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kPreThreads / 32; ++w) {
+      const int t = s_wsum[w];
+      if (w < warp) wbase += t;
+      total += t;
+    }
+    if (tid == 0) s_cta_base = (total > 0) ? atomicAdd(bin.cursor, total) : 0;
+    __syncthreads();
+    if (!live) return;
+    long long e = (long long)s_cta_base + wbase + incl - o_tiles;
+    bin.rank_base[i] = (int)e;
+    if (o_tiles > 0) {
+      // returning atomics in groups of four: four counters in flight per thread instead of one
+      const int w = rmaxx - rminx;
+      for (int t0 = 0; t0 < o_tiles; t0 += 4) {
+        int k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u;
+          if (t < o_tiles) {
+            const int ty = t / w, tx = t - ty * w;
+            k[u] = atomicAdd(bin.tile_count + (size_t)((rminy + ty) * f.grid_x + rminx + tx) * kCntStride, 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (t0 + u < o_tiles && e + u < bin.capacity) bin.rank[e + u] = k[u];
+        e += 4;
+      }
+    }
+  }
+
   radii[i] = o_radius;
   tiles_touched[i] = o_tiles;
   depths[i] = o_depth;
@@ -252,10 +307,10 @@ void gsb_make_framek(const gsb_frame* f, FrameK* k) {
   k->grid_y = (f->height + kTile - 1) / kTile;
 }
 
-GSB_API int gsb_preprocess(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const float* means,
-                           const float* scales, const float* rotations, const float* opacities, const float* shs,
-                           int32_t* radii, float* points_xy, float* depths, float* cov3Ds, float* rgb,
-                           float* conic_opacity, int32_t* tiles_touched, float* clamped_state) {
+int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
+                        const float* scales, const float* rotations, const float* opacities, const float* shs,
+                        int32_t* radii, float* points_xy, float* depths, float* cov3Ds, float* rgb,
+                        float* conic_opacity, int32_t* tiles_touched, float* clamped_state, const PreBin* bin) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && n >= 0, "gsb_preprocess: bad frame or n");
   if (n == 0) return GSB_OK;
@@ -266,8 +321,22 @@ GSB_API int gsb_preprocess(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32
   FrameK k;
   gsb_make_framek(f, &k);
   int grid = (int)gsb_div_up(n, kPreThreads);
-  GSB_LAUNCH(ctx, preprocess_kernel, grid, kPreThreads, 0, (cudaStream_t)s, k, n, means, scales, rotations, opacities,
-             shs, radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
-             reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state);
+  if (bin) {
+    GSB_LAUNCH(ctx, preprocess_kernel<true>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
+               radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
+               reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, *bin);
+  } else {
+    GSB_LAUNCH(ctx, preprocess_kernel<false>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
+               radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
+               reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, PreBin{});
+  }
   return GSB_OK;
+}
+
+GSB_API int gsb_preprocess(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const float* means,
+                           const float* scales, const float* rotations, const float* opacities, const float* shs,
+                           int32_t* radii, float* points_xy, float* depths, float* cov3Ds, float* rgb,
+                           float* conic_opacity, int32_t* tiles_touched, float* clamped_state) {
+  return gsb_preprocess_impl(ctx, (cudaStream_t)s, f, n, means, scales, rotations, opacities, shs, radii, points_xy,
+                             depths, cov3Ds, rgb, conic_opacity, tiles_touched, clamped_state, nullptr);
 }

@@ -96,8 +96,8 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
-                    const int* __restrict__ radii, const int* __restrict__ point_offsets, int grid_x, int grid_y,
-                    const int2* __restrict__ ranges, const int* __restrict__ rank,
+                    const int* __restrict__ radii, const int* __restrict__ rank_index, int index_is_exclusive,
+                    int grid_x, int grid_y, const int2* __restrict__ ranges, const int* __restrict__ rank,
                     unsigned long long* __restrict__ binned) {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n) return;
@@ -107,7 +107,8 @@ tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restric
   int rminx, rminy, rmaxx, rmaxy;
   gs_get_rect(p.x, p.y, (float)r, (float)grid_x, (float)grid_y, rminx, rminy, rmaxx, rmaxy);
   const unsigned long long v = ((unsigned long long)__float_as_uint(depths[tid]) << 32) | (unsigned)tid;
-  int64_t e = (tid > 0) ? point_offsets[tid - 1] : 0;
+  // first rank of this Gaussian: rank_base[tid] (fused counting pass) or the inclusive scan shifted by one
+  int64_t e = index_is_exclusive ? rank_index[tid] : ((tid > 0) ? rank_index[tid - 1] : 0);
   for (int y = rminy; y < rmaxy; ++y)
     for (int x = rminx; x < rmaxx; ++x) {
       binned[ranges[y * grid_x + x].x + rank[e]] = v;
@@ -210,44 +211,64 @@ tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __re
 
 constexpr int kMaxTileSort = 16384;
 
-// Bins and sorts; on return *num_rendered_host and *max_count_host are set (one stream sync).
-// Returns GSB_OK with *used = false when the caller must fall back to the radix path (segment too
-// long) -- in that case nothing but the counts has been written.
-int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                           const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
-                           int64_t* num_rendered_host, int* max_count_host) {
-  const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
-  const int num_tiles = gx * gy;
+// ---- host side -------------------------------------------------------------------------------
+// prepare: size and zero the per-tile counters (and the rank cursor of the fused counting pass)
+int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles) {
   int rc = gsb_grow(ctx, (void**)&ctx->tile_count, &ctx->tile_cap, (int64_t)num_tiles * kCntStride, sizeof(int32_t), s);
   if (rc != GSB_OK) return rc;
   // The arrival ranks live in vals_a (one int per duplicate).  Its capacity is a guess until D is
-  // known (previous frame's D); if it turns out too small the caller re-runs this pass.
+  // known (previous frame's D); if it turns out too small the caller re-runs the counting pass.
   if (ctx->bin_cap == 0 && (rc = gsb_reserve_binning(ctx, s, 4 * (int64_t)n + 1024)) != GSB_OK) return rc;
-  int* tile_count = ctx->tile_count;
-  GSB_CUDA(ctx, cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)num_tiles * kCntStride, s));
-  if (n > 0)
-    GSB_LAUNCH(ctx, tile_count_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
-               radii, point_offsets, gx, gy, ctx->bin_cap, tile_count, ctx->vals_a);
-  GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, tile_count, reinterpret_cast<int2*>(ranges),
+  GSB_CUDA(ctx, cudaMemsetAsync(ctx->tile_count, 0, sizeof(int32_t) * (size_t)num_tiles * kCntStride, s));
+  GSB_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars + 8, 0, sizeof(int32_t), s));
+  return GSB_OK;
+}
+
+// scan the counters into ranges, start the read-back of (D, max count) and mark it with an event
+int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges) {
+  GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
              ctx->d_scalars + 4);
   GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  GSB_CUDA(ctx, cudaStreamSynchronize(s));
+  GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
+  return GSB_OK;
+}
+
+// the one host wait of a frame: on the event, so work queued behind the read-back keeps running
+int gsb_tile_binning_wait(gsb_ctx* ctx, int64_t* num_rendered_host, int* max_count_host) {
+  GSB_CUDA(ctx, cudaEventSynchronize(ctx->ev_count));
   const int32_t total = ctx->h_scalars[4];
   *num_rendered_host = (total < 0) ? (int64_t)(uint32_t)total : (int64_t)total;
   *max_count_host = ctx->h_scalars[5];
   return GSB_OK;
 }
 
+// Stand-alone counting pass (gsb_bin_by_tile): on return *num_rendered_host and *max_count_host are set.
+int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
+                           const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
+                           int64_t* num_rendered_host, int* max_count_host) {
+  const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+  const int num_tiles = gx * gy;
+  int rc = gsb_tile_binning_prepare(ctx, s, n, num_tiles);
+  if (rc != GSB_OK) return rc;
+  if (n > 0)
+    GSB_LAUNCH(ctx, tile_count_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
+               radii, point_offsets, gx, gy, ctx->bin_cap, ctx->tile_count, ctx->vals_a);
+  if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges)) != GSB_OK) return rc;
+  return gsb_tile_binning_wait(ctx, num_rendered_host, max_count_host);
+}
+
+// rank_index: point_offsets (index_is_exclusive = 0) or the fused pass's rank_base (= 1)
 int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                          const float* depths, const int32_t* radii, const int32_t* point_offsets,
-                          const int32_t* ranges, int64_t num_rendered, int max_count, int32_t* point_list) {
+                          const float* depths, const int32_t* radii, const int32_t* rank_index,
+                          int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
+                          int32_t* point_list) {
   const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
   const int num_tiles = gx * gy;
   // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
   unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
   const int2* rg = reinterpret_cast<const int2*>(ranges);
   GSB_LAUNCH(ctx, tile_scatter_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
-             depths, radii, point_offsets, gx, gy, rg, ctx->vals_a, binned);
+             depths, radii, rank_index, index_is_exclusive, gx, gy, rg, ctx->vals_a, binned);
   (void)num_rendered;
   if (max_count <= 1024) {
     GSB_LAUNCH(ctx, tile_sort_kernel<1024>, num_tiles, 256, 1024 * 8, s, rg, binned, point_list);

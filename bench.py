@@ -222,6 +222,10 @@ def stage_table(torch, T, cam_index, target, iters=10):
             p(fb.cov3Ds), p(fb.clamped_state), p(fb.dL_dmean2D), p(fb.dL_dconic), p(fb.dL_dcolor), p(g["positions"]),
             p(g["shs"]), p(g["scales"]), p(g["rotations"]), None), 544 * N),
     }
+    # the two whole operators as the trainer calls them (gsb_forward fuses the binning's counting pass
+    # into preprocess and hides the scan behind the read-back of D, so it is faster than its stages)
+    stages["forward_whole"] = (lambda: (T.forward(cam_index), 0)[1], 348 * N + 88 * D + 24 * Pn + 8 * Tg)
+    stages["backward_whole"] = (lambda: (T.backward(cam_index, fb, T.grads), 0)[1], 588 * N + 40 * D + 20 * Pn)
     out = {}
     for name, (fn, nbytes) in stages.items():
         for _ in range(2):

@@ -207,8 +207,8 @@ constexpr int kSRow = 36;  // padded row length (floats) of the S / W tiles: con
 constexpr int kDRow = 12;  // row length of the result tile (6 moments, 2 pad, 3 colours, 1 pad)
 
 struct BwdSmem {
-  float4 a[256];   // x, y, conic.a, conic.b
-  float4 b[256];   // conic.c, opacity, power threshold, position in the tile's list (int bits)
+  float4 a[256];   // x, y, conic.a, conic.c   (two packed pairs: see gs_power_packed)
+  float4 b[256];   // conic.b, opacity, power threshold, position in the tile's list (int bits)
   float4 c[256];   // r, g, b, gid (int bits)
   int2 meta[256];  // position in the tile's list, block mask
   int smax[8];
@@ -276,7 +276,7 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
   const int bx0 = tile_x * kTile + (warp & 1) * 8, by0 = tile_y * kTile + (warp >> 1) * 4;  // block origin
   const int px = bx0 + (lane & 7);
   const int py = by0 + (lane >> 3);
-  const float pxf = (float)px, pyf = (float)py;
+  const gs_f2 npxy = gs_pack2(-(float)px, -(float)py);
   const int2 range = ranges[tile_id];
   const unsigned my_mask = gs_warp_mask(warp);
   const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
@@ -342,8 +342,8 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
         const float4 co = conic_opacity[gid];
         const float thr = gs_power_threshold(co.w);
         if (P.cull && !have) bmask = gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0);
-        ea = make_float4(p.x, p.y, co.x, co.y);
-        eb = make_float4(co.z, co.w, thr, __int_as_float(hi - 1 - tid));
+        ea = make_float4(p.x, p.y, co.x, co.z);
+        eb = make_float4(co.y, co.w, thr, __int_as_float(hi - 1 - tid));
         ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(gid));
       }
     }
@@ -360,41 +360,24 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     if (my_max <= hi - n_in) continue;
     // entries that touch this warp's block and lie inside its replay range (position < my_max)
     const int wn = warp_compact_hits(sm.meta, cnt, my_mask, my_max, lane, sm.widx[warp]);
-    int gslot = 0;              // slot of hit q in the current group
+    int gslot = 0;              // slot of the next hit in the current group
     float* pS = tS + lane;      // this lane's column of the S tile, row gslot (the W tile is 16 rows further)
-    for (int q = 0; q < wn; ++q) {
-      const int j = wlist[q];
-      const float4 a = sm.a[j];
-      const float4 b = sm.b[j];
-      const float dx = a.x - pxf;
-      const float dy = a.y - pyf;
-      float sv = 0.0f, wv = 0.0f;
-      const float power = gs_power(a.z, a.w, b.x, dx, dy);
-      // the replay limit (pixel replays the entry iff position < kept), backward.py:647 (power > 0)
-      // and the conservative exponent threshold
-      if (__float_as_int(b.w) < kept && !(power > 0.0f) && !(power < b.z)) {
-        const float G = exp_approx(power);
-        const float alpha = f_min(0.99f, b.y * G);
-        if (!(alpha < (1.0f / 255.0f))) {  // backward.py:655
-          const float4 c = sm.c[j];
-          const float inv_1ma = rcp_approx(1.0f - alpha);     // backward.py:658,680; 1 - alpha is in [0.01, 1]
-          T = T * inv_1ma;                                   // T_i
-          wv = alpha * T;                                    // d(channel)/d(colour), backward.py:672
-          const float dc = gs_dot3(c.x, c.y, c.z, dp0, dp1, dp2);
-          const float dL_dalpha = T * dc - gamma * inv_1ma;
-          gamma = fmaf(dc, wv, gamma);
-          sv = G * dL_dalpha;      // dL_dG = opacity * dL_dalpha is applied after the reduction
-        }
-      }
-      pS[0] = sv;
-      pS[kGrp * kSRow] = wv;
-      if (gslot != kGrp - 1 && q != wn - 1) {
-        ++gslot;
-        pS += kSRow;
-        continue;
-      }
 
-      // ---- group complete: reduce its (up to) 16 hits over the 32 pixels on the tensor cores ----
+    // One replayed hit whose alpha is known and >= 1/255 (backward.py:655-683): returns s, w.
+    auto replay_hit = [&](const float G, const float alpha, const int j, float& sv, float& wv) {
+      const float4 c = sm.c[j];
+      const float inv_1ma = rcp_approx(1.0f - alpha);     // backward.py:658,680; 1 - alpha is in [0.01, 1]
+      T = T * inv_1ma;                                   // T_i
+      wv = alpha * T;                                    // d(channel)/d(colour), backward.py:672
+      const float dc = gs_dot3(c.x, c.y, c.z, dp0, dp1, dp2);
+      const float dL_dalpha = T * dc - gamma * inv_1ma;
+      gamma = fmaf(dc, wv, gamma);
+      sv = G * dL_dalpha;      // dL_dG = opacity * dL_dalpha is applied after the reduction
+    };
+
+    // Group of `count` hits complete (rows 0 .. count-1 of the tiles, list entries qbase ..): reduce
+    // them over the 32 pixels on the tensor cores and add the results to the gradient arrays.
+    auto flush_group = [&](const int qbase, const int count) {
       __syncwarp();
       float dm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       // k-step ks (m16n8k4) covers the pixels (i = ks, r = 0..3); lane (fg, ft) supplies rows fg, fg + 8
@@ -444,10 +427,10 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       const unsigned nz = (__float_as_uint(m03.x) | __float_as_uint(m03.y) | __float_as_uint(m03.z) |
                            __float_as_uint(m03.w) | __float_as_uint(m45.x) | __float_as_uint(m45.y) |
                            __float_as_uint(col.x) | __float_as_uint(col.y) | __float_as_uint(col.z)) << 1;
-      if (lane <= gslot && nz != 0u) {
-        const int je = wlist[q - gslot + lane];
-        const float4 ga = sm.a[je];
-        const float4 gb = sm.b[je];
+      if (lane < count && nz != 0u) {
+        const int je = wlist[qbase + lane];
+        const float4 ga = sm.a[je];   // x, y, conic.a, conic.c
+        const float4 gb = sm.b[je];   // conic.b, opacity, ..
         const int gid = __float_as_int(sm.c[je].w);
         const float ux = ga.x - (float)bx0, uy = ga.y - (float)by0;   // dx = ux - i, dy = uy - r
         const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
@@ -460,8 +443,8 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
         atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
         atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
         atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
-        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, -o * (ga.z * Sdx + ga.w * Sdy) * ddelx_dx);   // backward.py:691-695
-        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, -o * (gb.x * Sdy + ga.w * Sdx) * ddely_dy);
+        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx);   // backward.py:691-695
+        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy);
         atomicAdd(dL_dconic + 4 * (size_t)gid + 0, -0.5f * o * Sdxx);                              // backward.py:698-703
         atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * o * Sdxy);
         atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * o * Sdyy);
@@ -470,7 +453,53 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       __syncwarp();  // results consumed before the next group overwrites the tile
       gslot = 0;
       pS = tS + lane;
+    };
+
+    // Two hits per iteration (the list is already in replay order): exponents share the packed
+    // FFMA2 sequence, the independent parts of the two hits overlap, the T / gamma recurrences stay
+    // sequential.  kGrp is even, so a pair never straddles a group.
+    int q = 0;
+    for (; q + 1 < wn; q += 2) {
+      const int jA = wlist[q], jB = wlist[q + 1];
+      const float4 aA = sm.a[jA], bA = sm.b[jA];
+      const float4 aB = sm.a[jB], bB = sm.b[jB];
+      const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);
+      const float pwB = gs_power_packed(gs_pack2(aB.x, aB.y), npxy, gs_pack2(aB.z, aB.w), bB.x);
+      // the replay limit (pixel replays the entry iff position < kept), backward.py:647 (power > 0)
+      // and the conservative exponent threshold
+      const bool actA = __float_as_int(bA.w) < kept && !(pwA > 0.0f) && !(pwA < bA.z);
+      const bool actB = __float_as_int(bB.w) < kept && !(pwB > 0.0f) && !(pwB < bB.z);
+      float svA = 0.0f, wvA = 0.0f, svB = 0.0f, wvB = 0.0f;
+      if (actA || actB) {
+        const float GA = exp_approx(pwA), GB = exp_approx(pwB);
+        const float alphaA = f_min(0.99f, bA.y * GA), alphaB = f_min(0.99f, bB.y * GB);
+        if (actA && !(alphaA < (1.0f / 255.0f))) replay_hit(GA, alphaA, jA, svA, wvA);  // backward.py:655
+        if (actB && !(alphaB < (1.0f / 255.0f))) replay_hit(GB, alphaB, jB, svB, wvB);
+      }
+      pS[0] = svA;
+      pS[kGrp * kSRow] = wvA;
+      pS[kSRow] = svB;
+      pS[kGrp * kSRow + kSRow] = wvB;
+      gslot += 2;
+      pS += 2 * kSRow;
+      if (gslot == kGrp) flush_group(q + 2 - kGrp, kGrp);
     }
+    if (q < wn) {  // odd tail
+      const int j = wlist[q];
+      const float4 a = sm.a[j], b4 = sm.b[j];
+      const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
+      float sv = 0.0f, wv = 0.0f;
+      if (__float_as_int(b4.w) < kept && !(power > 0.0f) && !(power < b4.z)) {
+        const float G = exp_approx(power);
+        const float alpha = f_min(0.99f, b4.y * G);
+        if (!(alpha < (1.0f / 255.0f))) replay_hit(G, alpha, j, sv, wv);
+      }
+      pS[0] = sv;
+      pS[kGrp * kSRow] = wv;
+      ++gslot;
+      ++q;
+    }
+    if (gslot > 0) flush_group(q - gslot, gslot);
   }
 }
 

@@ -22,6 +22,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
 int gsb_tile_binning_max();
 int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
 int g_blend_cull = 1;
+int g_tile_sort = 0;   // 0: bitonic network for every tile (default); 1: per-tile LSD radix sort (bitonic for tiles > 4096)
 int g_bwd_reduce = 2;
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
@@ -151,6 +152,10 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
   }
   if (!strcmp(name, "blend_cull") && (value == 0 || value == 1)) {
     g_blend_cull = value;
+    return GSB_OK;
+  }
+  if (!strcmp(name, "tile_sort") && (value == 0 || value == 1)) {
+    g_tile_sort = value;
     return GSB_OK;
   }
   if (!strcmp(name, "bwd_reduce") && value >= 0 && value <= 2) {

@@ -20,6 +20,9 @@
 // sort (sort.cu), which is also what the stage-level entry point gsb_sort_pairs64 runs.
 #include "common.cuh"
 
+extern int g_tile_sort;
+constexpr int kMaxTileSort = 16384;
+
 namespace {
 
 constexpr int kCntStride = 32;  // ints between two tiles' counters = one 128-byte line each
@@ -130,11 +133,11 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 template <int CAP>
 __global__ void __launch_bounds__(256)
 tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
-                 int* __restrict__ point_list) {
+                 int* __restrict__ point_list, int lo) {
   extern __shared__ __align__(16) unsigned long long s_key[];
   const int2 rg = ranges[blockIdx.x];
   const int count = rg.y - rg.x;
-  if (count <= 0) return;
+  if (count <= lo) return;  // empty, or a tile the radix kernel has sorted
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (count == 1) {
     if (tid == 0) point_list[rg.x] = (int)(unsigned)binned[rg.x];
@@ -207,9 +210,156 @@ tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __re
   for (int i = tid; i < count; i += 256) point_list[rg.x + i] = (int)(unsigned)s_key[i];
 }
 
+// One CTA per tile: stable LSD radix sort of the segment by the 32 depth bits (8 bits per pass, passes
+// whose digit is the same for every key are skipped -- the top byte of a positive float almost always
+// is), ids as payload, then ties (equal depth bits) put in ascending-id order: the order of the
+// reference's stable sort of (tile | depth) keys over an id-ordered list.  O(n) instead of the bitonic
+// network's O(n log^2 n); NOT the default -- see gsb_tile_binning_sort for the measurement.
+//   count phase   one shared-memory atomic per element on hist[digit][warp]
+//   scan          thread d scans digit d's eight warp counters, block-wide exclusive scan of the digits
+//   scatter       a warp walks its contiguous block in order; lanes with the same digit are ranked
+//                 by lane (match_any), the first of them advances hist[digit][warp]
+// Tiles whose count is outside (lo, hi] return at once (they belong to the bitonic kernel).
+template <int CAP>
+__global__ void __launch_bounds__(256)
+tile_radix_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
+                  int* __restrict__ point_list, int lo, int hi) {
+  // 12 bytes per element (two key buffers, two 16-bit payload buffers: the payload is the element's
+  // index in the unsorted segment, < CAP <= 4096) + the 8 KB histogram: 32 KB at CAP = 2048, so that
+  // seven CTAs share an SM -- the kernel is a chain of dependent shared-memory operations and lives
+  // on occupancy.
+  extern __shared__ __align__(16) unsigned s_u[];
+  unsigned* ks = s_u;                                                // keys, source
+  unsigned* kd = ks + CAP;                                           // keys, destination
+  unsigned* hist = kd + CAP;                                         // [256 digits][8 warps]
+  unsigned short* vs = reinterpret_cast<unsigned short*>(hist + 2048);  // payload, source
+  unsigned short* vd = vs + CAP;                                     // payload, destination
+  __shared__ unsigned s_red[8];
+  __shared__ unsigned s_wtot[8];
+  const int2 rg = ranges[blockIdx.x];
+  const int count = rg.y - rg.x;
+  if (count <= lo || count > hi) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (count == 1) {
+    if (tid == 0) point_list[rg.x] = (int)(unsigned)binned[rg.x];
+    return;
+  }
+  unsigned diff = 0u;
+  {
+    const unsigned k0 = (unsigned)(binned[rg.x] >> 32);
+    for (int i = tid; i < count; i += 256) {
+      const unsigned k = (unsigned)(binned[rg.x + i] >> 32);
+      ks[i] = k;
+      vs[i] = (unsigned short)i;
+      diff |= k ^ k0;
+    }
+  }
+  diff = __reduce_or_sync(0xffffffffu, diff);
+  if (lane == 0) s_red[warp] = diff;
+  __syncthreads();
+  diff = 0u;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) diff |= s_red[w];
+
+  const int per = (((count + 7) >> 3) + 31) & ~31;  // a warp's contiguous block, whole rounds of 32
+  const int wbeg = warp * per, wend = min(count, wbeg + per);
+  for (int shift = 0; shift < 32; shift += 8) {
+    if (((diff >> shift) & 255u) == 0u) continue;  // every key has the same digit here
+    // (the __syncthreads at the end of the previous pass / after the load orders the buffers)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hist[tid + 256 * k] = 0u;
+    __syncthreads();
+    for (int i = wbeg + lane; i < wend; i += 32) atomicAdd(&hist[((ks[i] >> shift) & 255u) * 8 + warp], 1u);
+    __syncthreads();
+    {
+      // thread d: exclusive scan of digit d's eight counters, then of the digit totals over the block
+      uint4 c0 = *reinterpret_cast<uint4*>(hist + tid * 8), c1 = *reinterpret_cast<uint4*>(hist + tid * 8 + 4);
+      const unsigned tot = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_wtot[warp] = inc;
+      __syncthreads();
+      unsigned base = inc - tot;
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (w < warp) base += s_wtot[w];
+      uint4 e0, e1;
+      e0.x = base;
+      e0.y = e0.x + c0.x;
+      e0.z = e0.y + c0.y;
+      e0.w = e0.z + c0.z;
+      e1.x = e0.w + c0.w;
+      e1.y = e1.x + c1.x;
+      e1.z = e1.y + c1.y;
+      e1.w = e1.z + c1.z;
+      *reinterpret_cast<uint4*>(hist + tid * 8) = e0;
+      *reinterpret_cast<uint4*>(hist + tid * 8 + 4) = e1;
+    }
+    __syncthreads();
+    for (int base_i = wbeg; base_i < wend; base_i += 32) {
+      const int i = base_i + lane;
+      const bool live = i < wend;
+      const unsigned key = live ? ks[i] : 0u;
+      const unsigned short val = live ? vs[i] : (unsigned short)0;
+      const unsigned digit = live ? ((key >> shift) & 255u) : 256u + lane;  // dead lanes match nobody
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      const int leader = __ffs(peers) - 1;
+      const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+      unsigned start = 0u;
+      if (live && lane == leader) {
+        start = hist[digit * 8 + warp];
+        hist[digit * 8 + warp] = start + __popc(peers);
+      }
+      start = __shfl_sync(0xffffffffu, start, leader);
+      if (live) {
+        kd[start + rank] = key;
+        vd[start + rank] = val;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    unsigned* t = ks;
+    ks = kd;
+    kd = t;
+    unsigned short* u = vs;
+    vs = vd;
+    vd = u;
+  }
+  // The payloads become Gaussian ids (kd is free: every pass ended with a swap).  Ties -- equal depth
+  // bits -- must come out in ascending id order: odd-even rounds, only if any tie exists.
+  unsigned* ids = kd;
+  bool tie = false;
+  for (int i = tid; i < count; i += 256) {
+    ids[i] = (unsigned)binned[rg.x + vs[i]];
+    if (i + 1 < count) tie |= (ks[i] == ks[i + 1]);
+  }
+  if (__syncthreads_or(tie)) {
+    bool swapped;
+    do {
+      swapped = false;
+#pragma unroll
+      for (int parity = 0; parity < 2; ++parity) {
+        for (int i = 2 * tid + parity; i + 1 < count; i += 512) {
+          if (ks[i] == ks[i + 1] && ids[i] > ids[i + 1]) {
+            const unsigned t = ids[i];
+            ids[i] = ids[i + 1];
+            ids[i + 1] = t;
+            swapped = true;
+          }
+        }
+        __syncthreads();
+      }
+    } while (__syncthreads_or(swapped));
+  }
+  for (int i = tid; i < count; i += 256) point_list[rg.x + i] = (int)ids[i];
+}
+
 }  // namespace
 
-constexpr int kMaxTileSort = 16384;
 
 // ---- host side -------------------------------------------------------------------------------
 // prepare: size and zero the per-tile counters (and the rank cursor of the fused counting pass)
@@ -270,18 +420,41 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   GSB_LAUNCH(ctx, tile_scatter_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
              depths, radii, rank_index, index_is_exclusive, gx, gy, rg, ctx->vals_a, binned);
   (void)num_rendered;
-  if (max_count <= 1024) {
-    GSB_LAUNCH(ctx, tile_sort_kernel<1024>, num_tiles, 256, 1024 * 8, s, rg, binned, point_list);
-  } else if (max_count <= 4096) {
-    GSB_LAUNCH(ctx, tile_sort_kernel<4096>, num_tiles, 256, 4096 * 8, s, rg, binned, point_list);
-  } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      GSB_CUDA(ctx, cudaFuncSetAttribute(tile_sort_kernel<kMaxTileSort>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kMaxTileSort * 8));
-      attr_set = true;
+  // Per-tile sort.  Default: the bitonic kernel.  g_tile_sort == 1 (A/B switch): the O(n) shared-memory
+  // radix sort for tiles of up to 4096 entries and the bitonic kernel for longer ones (each kernel
+  // skips the other's tiles).  Measured on a B200 at ~650 entries per tile the radix kernel executes
+  // half the instructions but is a chain of dependent shared-memory operations and barriers (28% of
+  // the issue slots used): 60 us against the bitonic network's 47 us.  It stays as the tested option.
+  constexpr int kRadixCap = 4096;
+  auto radix_smem = [](int cap) { return (size_t)(2 * cap + 2048) * sizeof(unsigned) + (size_t)2 * cap * sizeof(unsigned short); };
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSB_CUDA(ctx, cudaFuncSetAttribute(tile_sort_kernel<kMaxTileSort>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kMaxTileSort * 8));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(tile_radix_kernel<kRadixCap>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)radix_smem(kRadixCap)));
+    attr_set = true;
+  }
+  int bitonic_lo = 0;  // the bitonic kernel sorts tiles with more than this many entries
+  if (g_tile_sort == 1) {
+    if (max_count <= 1024) {
+      GSB_LAUNCH(ctx, tile_radix_kernel<1024>, num_tiles, 256, radix_smem(1024), s, rg, binned, point_list, 0, 1024);
+    } else if (max_count <= 2048) {
+      GSB_LAUNCH(ctx, tile_radix_kernel<2048>, num_tiles, 256, radix_smem(2048), s, rg, binned, point_list, 0, 2048);
+    } else {
+      GSB_LAUNCH(ctx, tile_radix_kernel<kRadixCap>, num_tiles, 256, radix_smem(kRadixCap), s, rg, binned, point_list, 0,
+                 kRadixCap);
     }
-    GSB_LAUNCH(ctx, tile_sort_kernel<kMaxTileSort>, num_tiles, 256, kMaxTileSort * 8, s, rg, binned, point_list);
+    if (max_count <= kRadixCap) return GSB_OK;
+    bitonic_lo = kRadixCap;
+  }
+  if (bitonic_lo == 0 && max_count <= 1024) {
+    GSB_LAUNCH(ctx, tile_sort_kernel<1024>, num_tiles, 256, 1024 * 8, s, rg, binned, point_list, bitonic_lo);
+  } else if (bitonic_lo == 0 && max_count <= 4096) {
+    GSB_LAUNCH(ctx, tile_sort_kernel<4096>, num_tiles, 256, 4096 * 8, s, rg, binned, point_list, bitonic_lo);
+  } else {
+    GSB_LAUNCH(ctx, tile_sort_kernel<kMaxTileSort>, num_tiles, 256, kMaxTileSort * 8, s, rg, binned, point_list,
+               bitonic_lo);
   }
   return GSB_OK;
 }

@@ -92,7 +92,8 @@ def test_duplicate_keys_and_ranges_vs_oracle(L, oracle):
 
 @pytest.mark.parametrize("n,w,h,smin,smax", [(20000, 320, 240, 0.005, 0.05),   # short lists  (<= 1024 per tile)
                                               (6000, 64, 48, 0.1, 0.4),         # long lists   (> 1024 per tile)
-                                              (9000, 32, 32, 0.5, 1.5)])        # every Gaussian in every tile (> 4096)
+                                              (9000, 32, 32, 0.5, 1.5),         # every Gaussian in every tile (> 4096)
+                                              (14000, 96, 64, 0.02, 0.6)])      # mixed: some tiles below, some above 4096
 def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax):
     """gsb_forward's per-tile counting sort + shared-memory sort and the global radix sort give the
     same point_list / ranges / n_contrib as the oracle's stable sort (incl. exact depth ties)."""
@@ -108,12 +109,16 @@ def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax):
         oracle.set_threads(1)
     longest = int(np.diff(ob["ranges"], axis=1).max())
     ctx = L.context()
-    for mode in (0, 1):
+    # (binning, tile_sort): bitonic per tile (default), per-tile radix sort (bitonic for tiles > 4096),
+    # global radix sort
+    for mode, tile_sort in ((0, 0), (0, 1), (1, 0)):
         ctx.set_option("binning", mode)
+        ctx.set_option("tile_sort", tile_sort)
         try:
             img, _, buf = forward.render_gaussians(**kw)
         finally:
             ctx.set_option("binning", 0)
+            ctx.set_option("tile_sort", 0)
         for k in ("point_offsets", "point_list", "ranges", "n_contrib", "radii"):
-            assert np.array_equal(buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]), (mode, k, longest)
+            assert np.array_equal(buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]), (mode, tile_sort, k, longest)
         assert np.abs(img.cpu().numpy() - o_img).max() <= 1e-4

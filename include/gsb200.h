@@ -213,10 +213,11 @@ int gsb_adam_step_peers(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, in
 int gsb_fill_f32(gsb_ctx* ctx, gsb_stream s, float* dst, int64_t count, float value);
 
 /* Diagnostic (no reference counterpart): the Adam kernels divide with a rescaled fast path instead of
- * the compiler's range-checked `/`; out_fast[i] = that division of a[i] by b[i] (b > 0),
- * out_ref[i] = a[i] / b[i].  The two are bit-identical for every input. */
+ * the compiler's range-checked `/`; out_fast[i] = that division of a[i] by b[i] (b > 0), out_const[i]
+ * = the variant for host-known divisors (reciprocal passed in), out_ref[i] = a[i] / b[i].  The three
+ * are bit-identical for every input. */
 int gsb_selftest_div(gsb_ctx* ctx, gsb_stream s, int64_t count, const float* a, const float* b, float* out_fast,
-                     float* out_ref);
+                     float* out_const, float* out_ref);
 /* out += in (view-batch gradient accumulation; no reference counterpart: batch size is 1 there) */
 int gsb_accumulate_f32(gsb_ctx* ctx, gsb_stream s, float* out, const float* in, int64_t count);
 

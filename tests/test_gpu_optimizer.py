@@ -211,14 +211,17 @@ def test_adam_division_is_bit_identical_to_the_operator(gs):
     # small numerators against each divisor class as well (the case Adam is in all the time)
     a[1::3] = (a[1::3] * np.float32(1e-20)).astype(np.float32)
     ta, tb = _cuda(a), _cuda(b)
-    fast, ref = torch.empty_like(ta), torch.empty_like(ta)
+    fast, const, ref = torch.empty_like(ta), torch.empty_like(ta), torch.empty_like(ta)
     ctx.check(_lib.lib().gsb_selftest_div(ctx.h, _lib.stream_ptr(ctx.device_index), n, _lib.ptr(ta), _lib.ptr(tb),
-                                          _lib.ptr(fast), _lib.ptr(ref)))
+                                          _lib.ptr(fast), _lib.ptr(const), _lib.ptr(ref)))
     torch.cuda.synchronize()
     f, r = fast.cpu().numpy().view(np.uint32), ref.cpu().numpy().view(np.uint32)
     both_nan = np.isnan(fast.cpu().numpy()) & np.isnan(ref.cpu().numpy())
     bad = (f != r) & ~both_nan
     assert not bad.any(), f"{bad.sum()} of {n} quotients differ, e.g. a={a[bad][:3]} b={b[bad][:3]}"
+    c = const.cpu().numpy().view(np.uint32)
+    bad = (c != r) & ~(np.isnan(const.cpu().numpy()) & np.isnan(ref.cpu().numpy()))
+    assert not bad.any(), f"{bad.sum()} of {n} reciprocal-based quotients differ, e.g. a={a[bad][:3]} b={b[bad][:3]}"
     # and against the host's IEEE division
     with np.errstate(all="ignore"):
         host = (a / b).view(np.uint32)

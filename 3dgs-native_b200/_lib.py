@@ -151,6 +151,9 @@ def to_device(x, dtype=torch.float32, device=None, shape=None):
     untouched when already contiguous and of the right dtype (like ``wp.array`` inputs do)."""
     if x is None:
         return None
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == dtype and x.is_contiguous() and not x.requires_grad \
+            and (device is None or x.device == device):
+        return x if shape is None else x.view(shape)       # the common case in a training loop: nothing to do
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     if isinstance(x, torch.Tensor):

@@ -348,21 +348,25 @@ def ours(args):
     if not args.no_e2e:
         pinned = [torch.from_numpy(t).pin_memory() for t in targets]
         copy_stream = torch.cuda.Stream(device=dev)
+        tgt_dev = [torch.empty((h, w, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        tgt_ready = [torch.cuda.Event() for _ in range(2)]
         P, G, M, V = T.params, T.grads, T.adam_m, T.adam_v
         bg = np.zeros(3, dtype=np.float32)
 
         def e2e_step(it):
             ci = batch(it)[rank]
             cam = cams[ci]
-            # H2D of the step's input, on a copy stream: the forward does not read the target, so the
-            # 7.7 MB transfer (~150 us over PCIe) runs beside it; the loss kernel waits for it.
-            main = torch.cuda.current_stream()
-            with torch.cuda.stream(copy_stream):
-                tgt = pinned[ci].to(dev, non_blocking=True)
-                ready = copy_stream.record_event()
             img, _depth, buf = gf.render_gaussians(**scene.render_kwargs(P.as_dict(), cam, background=bg))
+            # H2D of the step's input from pinned memory, on a copy stream, issued as soon as the forward
+            # call returns (its tile kernel is still running): the forward does not read the target, so
+            # the 7.7 MB transfer (~150 us over PCIe) runs beside it; the loss kernel waits for it.
+            # Two device buffers, reused: steps end with a host read of the loss, so buffer k is free.
+            main = torch.cuda.current_stream()
+            tgt, ready = tgt_dev[it & 1], tgt_ready[it & 1]
+            with torch.cuda.stream(copy_stream):
+                tgt.copy_(pinned[ci], non_blocking=True)
+                ready.record(copy_stream)
             main.wait_event(ready)
-            tgt.record_stream(main)
             loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0)
             g = gb.backward(**scene.backward_kwargs(P.as_dict(), cam, buf, dpix, background=bg))
             if world > 1:

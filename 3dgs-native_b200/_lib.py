@@ -65,6 +65,8 @@ _SIGS = {
     "gsb_prune_mask": (C.c_int, [vp, vp, i32, vp, f32, vp]),
     "gsb_compact_gaussians": (C.c_int, [vp, vp, i32, i32, vp, vp] + [vp] * 10),
     "gsb_l1_loss_grad": (C.c_int, [vp, vp, i64, vp, vp, f32, vp, vp]),
+    "gsb_ssim": (C.c_int, [vp, vp, i32, i32, vp, vp, vp]),
+    "gsb_depth_loss": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -34,3 +34,31 @@ def compute_image_gradients(rendered, target, lambda_dssim=0.2):
     """loss.py:217-244: d(loss)/d(pixel) = (1 - lambda_dssim)/(3HW) * sign(rendered - target), with
     Warp's sign(0) = +1.  The SSIM term is a TODO in the reference and contributes nothing."""
     return l1_loss_and_gradients(rendered, target, lambda_dssim)[1]
+
+
+def ssim(rendered, target) -> float:
+    """loss.py:178-215: mean over the pixels of the 11x11-window SSIM (mean of the three channels).
+    Synchronises: returns a Python float like the reference.  (The reference has no SSIM gradient:
+    ``compute_image_gradients`` ignores the term, loss.py:243.)"""
+    ctx = _lib.context()
+    dev = torch.device("cuda", ctx.device_index)
+    r = _lib.to_device(rendered, device=dev)
+    t = _lib.to_device(target, device=dev)
+    H, W = r.shape[0], r.shape[1]
+    s = torch.empty(1, dtype=torch.float64, device=dev)
+    ctx.check(_lib.lib().gsb_ssim(ctx.h, _lib.stream_ptr(ctx.device_index), W, H, _lib.ptr(r), _lib.ptr(t), _lib.ptr(s)))
+    return float(s.item()) / (W * H)
+
+
+def depth_loss(rendered_depth, target_depth, depth_mask) -> float:
+    """loss.py:270-306: mean of |rendered - target| * mask over the pixels (inverse depths)."""
+    ctx = _lib.context()
+    dev = torch.device("cuda", ctx.device_index)
+    r = _lib.to_device(rendered_depth, device=dev)
+    t = _lib.to_device(target_depth, device=dev)
+    m = _lib.to_device(depth_mask, device=dev)
+    H, W = r.shape[0], r.shape[1]
+    s = torch.empty(1, dtype=torch.float64, device=dev)
+    ctx.check(_lib.lib().gsb_depth_loss(ctx.h, _lib.stream_ptr(ctx.device_index), H * W, _lib.ptr(r), _lib.ptr(t),
+                                        _lib.ptr(m), _lib.ptr(s)))
+    return float(s.item()) / (W * H)

@@ -268,6 +268,19 @@ int gsb_compact_gaussians(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t out_n, 
 int gsb_l1_loss_grad(gsb_ctx* ctx, gsb_stream s, int64_t count, const float* rendered, const float* target,
                      float l1_weight, float* pixel_grad, double* loss_sum);
 
+/* replaces gaussian_kernel + ssim_kernel + ssim() (loss.py:33-119, 178-215; "next" row 8f-4 -- dead
+ * code in the reference's step loop, train.py:967-974, and without a gradient there, loss.py:243):
+ * *ssim_sum (device double, zeroed here) receives the sum over the pixels of the mean-over-channels
+ * SSIM in an 11x11 window truncated at the border, with the reference's weights as written;
+ * ssim = *ssim_sum / (W*H).  rendered / target: float[H][W][3]. */
+int gsb_ssim(gsb_ctx* ctx, gsb_stream s, int32_t width, int32_t height, const float* rendered, const float* target,
+             double* ssim_sum);
+
+/* replaces depth_loss_kernel + depth_loss() (loss.py:248-306): *loss_sum (device double, zeroed here)
+ * = sum |rendered_depth - target_depth| * depth_mask over count = W*H pixels; loss = sum / (W*H). */
+int gsb_depth_loss(gsb_ctx* ctx, gsb_stream s, int64_t count, const float* rendered_depth, const float* target_depth,
+                   const float* depth_mask, double* loss_sum);
+
 #ifdef __cplusplus
 }
 #endif

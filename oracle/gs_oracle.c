@@ -1247,6 +1247,77 @@ GSO_API void gso_l1_grad(int W, int H, const float* rendered, const float* targe
   }
 }
 
+/* loss.py:33-45 gaussian_kernel + loss.py:47-119 ssim_kernel + loss.py:178-215 ssim(): per pixel an
+ * 11x11 window truncated at the image border, weights exp(-x^2 / (2 sigma^2)) (sigma = 1.5) per axis,
+ * normalised by the weights actually summed; the per-pixel value is the mean of the three channels'
+ * SSIM; serial fp32 accumulation in thread order i (x) outer, j (y) inner, then float(sum)/(W*H). */
+GSO_API double gso_ssim(int W, int H, const float* rendered, const float* target) {
+  const int window_size = 11, half_window = window_size / 2;
+  const float sigma = 1.5f;
+  float gw[11];
+  for (int i = 0; i < window_size; ++i) {
+    int x = i - window_size / 2;
+    gw[i] = gs_exp(-1.0f * (float)(x * x) / (2.0f * sigma * sigma));
+  }
+  const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+  float acc = 0.0f;
+  for (int i = 0; i < W; ++i)
+    for (int j = 0; j < H; ++j) {
+      float mu1[3] = {0, 0, 0}, mu2[3] = {0, 0, 0}, s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0}, s12[3] = {0, 0, 0};
+      float weight_sum = 0.0f;
+      int y0 = j - half_window < 0 ? 0 : j - half_window, y1 = j + half_window + 1 > H ? H : j + half_window + 1;
+      int x0 = i - half_window < 0 ? 0 : i - half_window, x1 = i + half_window + 1 > W ? W : i + half_window + 1;
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          int wy = y - j < 0 ? j - y : y - j, wx = x - i < 0 ? i - x : x - i;
+          /* loss.py:84: weights are indexed by |offset| (0..5), i.e. the LEFT half of the kernel array:
+           * gaussian_weights[k] = exp(-(k-5)^2 / 4.5), so the centre tap gets exp(-25/4.5) and the
+           * farthest tap 1.0 -- reproduced as written */
+          float w = gw[wx] * gw[wy];
+          size_t p = ((size_t)y * W + x) * 3;
+          for (int c = 0; c < 3; ++c) {
+            float p1 = rendered[p + c], p2 = target[p + c];
+            mu1[c] = mu1[c] + p1 * w;
+            mu2[c] = mu2[c] + p2 * w;
+            s1[c] = s1[c] + (p1 * p1) * w;
+            s2[c] = s2[c] + (p2 * p2) * w;
+            s12[c] = s12[c] + (p1 * p2) * w;
+          }
+          weight_sum = weight_sum + w;
+        }
+      float ssim_c[3];
+      for (int c = 0; c < 3; ++c) {
+        float m1 = mu1[c], m2 = mu2[c], v1 = s1[c], v2 = s2[c], v12 = s12[c];
+        if (weight_sum > 0.0f) {
+          m1 = m1 / weight_sum;
+          m2 = m2 / weight_sum;
+          v1 = v1 / weight_sum;
+          v2 = v2 / weight_sum;
+          v12 = v12 / weight_sum;
+        }
+        v1 = v1 - m1 * m1;
+        v2 = v2 - m2 * m2;
+        v12 = v12 - m1 * m2;
+        ssim_c[c] = ((2.0f * m1 * m2 + c1) * (2.0f * v12 + c2)) / ((m1 * m1 + m2 * m2 + c1) * (v1 + v2 + c2));
+      }
+      float ssim_val = (ssim_c[0] + ssim_c[1] + ssim_c[2]) / 3.0f;
+      acc += ssim_val;
+    }
+  return (double)acc / ((double)W * (double)H);
+}
+
+/* loss.py:248-268 depth_loss_kernel + 270-306 depth_loss(): sum |rendered - target| * mask, / (W*H) */
+GSO_API double gso_depth_loss(int W, int H, const float* rendered_depth, const float* target_depth,
+                              const float* depth_mask) {
+  float acc = 0.0f;
+  for (int i = 0; i < W; ++i)
+    for (int j = 0; j < H; ++j) {
+      size_t p = (size_t)j * W + i;
+      acc += fabsf(rendered_depth[p] - target_depth[p]) * depth_mask[p];
+    }
+  return (double)acc / ((double)W * (double)H);
+}
+
 /* forward.py:589-627 track_pixel_stats.  Provably a no-op after wp_render_gaussians (SURVEY
  * 8a F12); restated so that a test can assert exactly that.  Returns #elements modified. */
 GSO_API int gso_track_pixel_stats(int W, int H, const float* image, const float* bg, float* final_Ts, int* n_contrib) {

@@ -51,6 +51,8 @@ def lib():
         _lib.gso_randf.restype = C.c_float
         _lib.gso_randf.argtypes = [C.c_uint32]
         _lib.gso_l1_loss.restype = C.c_double
+        _lib.gso_ssim.restype = C.c_double
+        _lib.gso_depth_loss.restype = C.c_double
     return _lib
 
 
@@ -409,6 +411,20 @@ def compute_image_gradients(rendered, target, lambda_dssim=0.2):
     l1_weight = (1.0 - lambda_dssim) / (H * W * 3.0)                 # loss.py:236 (python double)
     lib().gso_l1_grad(W, H, _p(r), _p(t), _cf(l1_weight), _p(g))
     return g
+
+
+def ssim(rendered, target) -> float:
+    """loss.py:178-215."""
+    r, t = _f32(rendered), _f32(target)
+    H, W = r.shape[0], r.shape[1]
+    return float(lib().gso_ssim(W, H, _p(r), _p(t)))
+
+
+def depth_loss(rendered_depth, target_depth, depth_mask) -> float:
+    """loss.py:270-306."""
+    r, t, m = _f32(rendered_depth), _f32(target_depth), _f32(depth_mask)
+    H, W = r.shape[0], r.shape[1]
+    return float(lib().gso_depth_loss(W, H, _p(r), _p(t), _p(m)))
 
 
 def get_lr(initial_lr, final_lr_factor, iteration, total_iterations):

@@ -303,6 +303,26 @@ def case_loss():
     print("ref_loss written", l1)
 
 
+def case_loss2():
+    """loss.py ssim (11x11 Gaussian window, sigma 1.5, truncated at the borders) and depth_loss -- dead code in
+    train.py (967-974) but part of loss.py's surface."""
+    rng = np.random.default_rng(22)
+    H, W = 17, 23
+    r = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    t = np.clip(r + rng.normal(0, 0.1, (H, W, 3)), 0, 1).astype(np.float32)
+    t[3:6, 4:9] = r[3:6, 4:9]
+    s1 = ref_loss.ssim(r, t)
+    s_same = ref_loss.ssim(r, r)
+    rd = rng.uniform(0.1, 2.0, (H, W)).astype(np.float32)
+    td = rng.uniform(0.1, 2.0, (H, W)).astype(np.float32)
+    mask = (rng.uniform(0, 1, (H, W)) > 0.3).astype(np.float32)
+    dl = ref_loss.depth_loss(rd, td, mask)
+    np.savez_compressed(os.path.join(HERE, "ref_loss2.npz"), rendered=r, target=t, ssim=np.float64(s1),
+                        ssim_same=np.float64(s_same), rendered_depth=rd, target_depth=td, depth_mask=mask,
+                        depth_loss=np.float64(dl))
+    print("ref_loss2 written", s1, s_same, dl)
+
+
 def case_misc():
     """LR schedule, init kernel, exclusive scan + prefix sum helpers."""
     from scheduler import LRScheduler
@@ -322,6 +342,6 @@ def case_misc():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lego_small", "lego_deg1", "lego_bg", "example_scene", "adam", "densify", "loss", "misc"]
+    which = sys.argv[1:] or ["lego_small", "lego_deg1", "lego_bg", "example_scene", "adam", "densify", "loss", "loss2", "misc"]
     for w in which:
         globals()["case_" + w]()

@@ -227,3 +227,28 @@ def test_adam_division_is_bit_identical_to_the_operator(gs):
         host = (a / b).view(np.uint32)
     ok = (host == f) | both_nan
     assert ok.all(), f"{(~ok).sum()} quotients differ from the host division"
+
+
+def test_ssim_and_depth_loss_vs_golden_and_oracle(gs, golden_dir, oracle):
+    """loss.ssim / loss.depth_loss against the values the reference's source produced under the Warp shim
+    (small image, border windows everywhere) and against the oracle at 800x800 and on a ragged size."""
+    g = np.load(os.path.join(golden_dir, "ref_loss2.npz"))
+    assert abs(gs.loss.ssim(g["rendered"], g["target"]) - float(g["ssim"])) <= 2e-6
+    assert abs(gs.loss.ssim(g["rendered"], g["rendered"]) - 1.0) <= 2e-6
+    assert abs(gs.loss.depth_loss(g["rendered_depth"], g["target_depth"], g["depth_mask"]) - float(g["depth_loss"])) <= 2e-6
+    rng = np.random.default_rng(5)
+    for (h, w) in ((800, 800), (37, 101), (5, 3)):
+        r = rng.uniform(0, 1, (h, w, 3)).astype(np.float32)
+        t = np.clip(r + rng.normal(0, 0.2, (h, w, 3)), 0, 1).astype(np.float32)
+        t[: h // 3] = r[: h // 3]
+        want = oracle.ssim(r, t)
+        got = gs.loss.ssim(_cuda(r), _cuda(t))
+        # the oracle (like the reference) adds the W*H per-pixel values into ONE binary32 accumulator:
+        # at 640k pixels that sum alone carries ~2e-5 of rounding; the kernel accumulates in double
+        assert abs(got - want) <= 1e-7 * h * w + 5e-6, (h, w, got, want)
+        rd = rng.uniform(0.05, 3.0, (h, w)).astype(np.float32)
+        td = rng.uniform(0.05, 3.0, (h, w)).astype(np.float32)
+        m = (rng.uniform(0, 1, (h, w)) > 0.5).astype(np.float32)
+        want = oracle.depth_loss(rd, td, m)
+        got = gs.loss.depth_loss(rd, td, m)
+        assert abs(got - want) <= 1e-7 * h * w + 5e-6, (h, w, got, want)

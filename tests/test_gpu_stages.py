@@ -93,7 +93,8 @@ def test_duplicate_keys_and_ranges_vs_oracle(L, oracle):
 @pytest.mark.parametrize("n,w,h,smin,smax", [(20000, 320, 240, 0.005, 0.05),   # short lists  (<= 1024 per tile)
                                               (6000, 64, 48, 0.1, 0.4),         # long lists   (> 1024 per tile)
                                               (9000, 32, 32, 0.5, 1.5),         # every Gaussian in every tile (> 4096)
-                                              (14000, 96, 64, 0.02, 0.6)])      # mixed: some tiles below, some above 4096
+                                              (14000, 96, 64, 0.02, 0.6),       # mixed: some tiles below, some above 4096
+                                              (18000, 16, 16, 1.0, 2.0)])       # one tile, > 16384 entries: radix fallback
 def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax):
     """gsb_forward's per-tile counting sort + shared-memory sort and the global radix sort give the
     same point_list / ranges / n_contrib as the oracle's stable sort (incl. exact depth ties)."""

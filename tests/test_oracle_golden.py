@@ -148,3 +148,13 @@ def test_misc_matches_reference_source(oracle, golden_dir):
     p = oracle.init_gaussian_params(32, 0.1)
     for k in oracle.PARAM_KEYS:
         assert np.array_equal(p[k], g["init_" + k].reshape(p[k].shape)), k
+
+
+def test_ssim_and_depth_loss_match_reference_source(golden_dir):
+    """loss.py ssim() / depth_loss() run under the Warp shim (tests/golden/make_golden.py case_loss2):
+    the oracle restates them, incl. the |offset|-indexed window weights (centre tap lightest)."""
+    import oracle as O
+    g = np.load(os.path.join(golden_dir, "ref_loss2.npz"))
+    assert abs(O.ssim(g["rendered"], g["target"]) - float(g["ssim"])) <= 1e-6
+    assert abs(O.ssim(g["rendered"], g["rendered"]) - 1.0) <= 1e-6 and abs(float(g["ssim_same"]) - 1.0) <= 1e-6
+    assert abs(O.depth_loss(g["rendered_depth"], g["target_depth"], g["depth_mask"]) - float(g["depth_loss"])) <= 1e-6

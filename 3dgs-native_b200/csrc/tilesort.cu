@@ -133,11 +133,11 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 template <int CAP>
 __global__ void __launch_bounds__(256)
 tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
-                 int* __restrict__ point_list, int lo) {
+                 int* __restrict__ point_list, int lo, int hi) {
   extern __shared__ __align__(16) unsigned long long s_key[];
   const int2 rg = ranges[blockIdx.x];
   const int count = rg.y - rg.x;
-  if (count <= lo) return;  // empty, or a tile the radix kernel has sorted
+  if (count <= lo || count > hi) return;  // empty, or a tile another launch sorts
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (count == 1) {
     if (tid == 0) point_list[rg.x] = (int)(unsigned)binned[rg.x];
@@ -448,13 +448,19 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
     if (max_count <= kRadixCap) return GSB_OK;
     bitonic_lo = kRadixCap;
   }
+  // The shared-memory footprint is the launch's capacity (8 B per entry), so a frame with a few very
+  // long lists sorts the short ones with the small-footprint instance (several CTAs per SM) and only
+  // the long ones with the 128 KB instance.
+  const int kBig = 1 << 30;
   if (bitonic_lo == 0 && max_count <= 1024) {
-    GSB_LAUNCH(ctx, tile_sort_kernel<1024>, num_tiles, 256, 1024 * 8, s, rg, binned, point_list, bitonic_lo);
-  } else if (bitonic_lo == 0 && max_count <= 4096) {
-    GSB_LAUNCH(ctx, tile_sort_kernel<4096>, num_tiles, 256, 4096 * 8, s, rg, binned, point_list, bitonic_lo);
+    GSB_LAUNCH(ctx, tile_sort_kernel<1024>, num_tiles, 256, 1024 * 8, s, rg, binned, point_list, 0, kBig);
+  } else if (max_count <= 4096) {
+    GSB_LAUNCH(ctx, tile_sort_kernel<4096>, num_tiles, 256, 4096 * 8, s, rg, binned, point_list, bitonic_lo, kBig);
   } else {
-    GSB_LAUNCH(ctx, tile_sort_kernel<kMaxTileSort>, num_tiles, 256, kMaxTileSort * 8, s, rg, binned, point_list,
-               bitonic_lo);
+    if (bitonic_lo < 4096)
+      GSB_LAUNCH(ctx, tile_sort_kernel<4096>, num_tiles, 256, 4096 * 8, s, rg, binned, point_list, bitonic_lo, 4096);
+    GSB_LAUNCH(ctx, tile_sort_kernel<kMaxTileSort>, num_tiles, 256, kMaxTileSort * 8, s, rg, binned, point_list, 4096,
+               kBig);
   }
   return GSB_OK;
 }

@@ -162,6 +162,9 @@ class Trainer:
         self.losses = []
 
     # ---- state -------------------------------------------------------------------------------
+    exchange_events = None   # set to a list to collect (start, end) CUDA events around exchange_and_step
+    exchange_parts = []      # with it: (before barrier, after barrier, after kernel, after barrier) per step
+
     def _pick_exchange(self, want):
         if self.world_size <= 1:
             return "none"
@@ -306,13 +309,25 @@ class Trainer:
         use_mc = self.exchange == "multimem"
         g_mc = int(G.multicast_ptr) if use_mc else 0
         p_mc = int(P.multicast_ptr) if use_mc else 0
+        ev = None
+        if self.exchange_events is not None:
+            import torch
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         G.barrier(channel=0)        # every rank's backward has finished writing its gradients
+        if ev:
+            ev[1].record()
         self.ctx.check(_lib.lib().gsb_adam_step_peers(
             self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, g_mc, p_mc,
             _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
             lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
             self.config["adam_epsilon"], iteration))
+        if ev:
+            ev[2].record()
         P.barrier(channel=1)        # every rank's parameter shard has landed everywhere
+        if ev:
+            ev[3].record()
+            self.exchange_parts.append(ev)
 
     def train_step(self, iteration: int, cam_indices, targets=None, densify=True):
         """One step on a batch of views.  ``cam_indices`` is the GLOBAL batch; this rank takes the
@@ -325,7 +340,15 @@ class Trainer:
             ci = cam_indices[b]
             tgt = targets[b] if targets is not None else self.targets[ci]
             fb = self.accumulate_view(ci, tgt, first=(j == 0))
-        self.exchange_and_step(iteration)
+        if self.exchange_events is not None:     # bench.py: device time of the exchange + Adam part
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.exchange_and_step(iteration)
+            e1.record()
+            self.exchange_events.append((e0, e1))
+        else:
+            self.exchange_and_step(iteration)
         if densify:
             self.densification_and_pruning(iteration)
         return fb.loss_sum

@@ -528,7 +528,7 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
                n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, masks);
     return GSB_OK;
   }
-  static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in, once per process
+  bool& attr_set = ctx->smem_optin_blend_bwd;  // > 48 KB of dynamic shared memory needs the opt-in (per device)
   if (!attr_set) {
     GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(BwdSmem)));

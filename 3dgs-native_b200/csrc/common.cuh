@@ -23,6 +23,8 @@ struct gsb_ctx {
   int num_sms = 148;
   char err[512] = {0};
   int64_t launches = 0;
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: done once per context, not per process
+  bool smem_optin_blend_bwd = false, smem_optin_radix = false, smem_optin_tilesort = false;
 
   // binning scratch (grow-only): sort double buffers
   int64_t* keys_a = nullptr;

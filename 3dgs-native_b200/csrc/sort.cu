@@ -230,7 +230,7 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
   if (n > GSB_MAX_RENDERED) return gsb_set_error(ctx, GSB_ERR_TOO_MANY, "radix sort: %lld pairs exceed 2^30-1", (long long)n);
   if (begin_bit < 0 || end_bit > 64 || end_bit <= begin_bit)
     return gsb_set_error(ctx, GSB_ERR_INVALID, "radix sort: bad bit range [%d,%d)", begin_bit, end_bit);
-  static bool attr_set = false;
+  bool& attr_set = ctx->smem_optin_radix;
   if (!attr_set) {
     GSB_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ScatterSmem)));

@@ -427,7 +427,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   // the issue slots used): 60 us against the bitonic network's 47 us.  It stays as the tested option.
   constexpr int kRadixCap = 4096;
   auto radix_smem = [](int cap) { return (size_t)(2 * cap + 2048) * sizeof(unsigned) + (size_t)2 * cap * sizeof(unsigned short); };
-  static bool attr_set = false;
+  bool& attr_set = ctx->smem_optin_tilesort;
   if (!attr_set) {
     GSB_CUDA(ctx, cudaFuncSetAttribute(tile_sort_kernel<kMaxTileSort>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMaxTileSort * 8));

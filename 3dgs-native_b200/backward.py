@@ -12,12 +12,17 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
              scale_modifier=1.0, viewmatrix=None, projmatrix=None, tan_fovx=0.5, tan_fovy=0.5,
              image_height=256, image_width=256, campos=None, radii=None, means2D=None, conic_opacity=None,
              rgb=None, clamped=None, cov3Ds=None, geom_buffer=None, binning_buffer=None, img_buffer=None,
-             degree=3, debug=False):
+             degree=3, debug=False, out=None):
     """Gradients of all Gaussian parameters.  Same arguments and the same 9-key result dict as the
     reference.  Like there, ``img_buffer`` (ranges, final_Ts, n_contrib) and ``binning_buffer``
     (point_list) are required, ``scale_modifier`` is accepted but not used by the covariance
     backward (quirk G3), and ``dL_dcov3D`` is returned as zeros.  ``dL_dshs`` always has 16 rows per
-    Gaussian (the reference under-allocates it for degree < 3 and then writes out of bounds)."""
+    Gaussian (the reference under-allocates it for degree < 3 and then writes out of bounds).
+
+    ``out`` (not a reference argument; default None = allocate like the reference does): a dict with
+    any of the nine result keys mapping to preallocated contiguous float32 CUDA tensors of the right
+    size, which then receive those results -- e.g. views of a flat gradient buffer that a multi-GPU
+    exchange reads in place."""
     if img_buffer is None or binning_buffer is None:
         raise ValueError("backward() needs img_buffer{ranges,final_Ts,n_contrib} and binning_buffer{point_list} "
                          "(backward.py:1084-1090)")
@@ -57,9 +62,21 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
     dpix = td(dL_dpixels, shape=(H, W, 3))
     frame = _lib.make_frame(viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, W, H, background, degree, True,
                             scale_modifier)
-    e = lambda *shape: torch.empty(shape, dtype=f32, device=dev)  # noqa: E731
-    g = {"dL_dmean3D": e(n, 3), "dL_dcolor": e(n, 3), "dL_dshs": e(n * 16, 3), "dL_dopacity": e(n),
-         "dL_dscale": e(n, 3), "dL_drot": e(n, 4), "dL_dmean2D": e(n, 3), "dL_dconic": e(n, 4), "dL_dcov3D": e(n, 6)}
+    shapes = {"dL_dmean3D": (n, 3), "dL_dcolor": (n, 3), "dL_dshs": (n * 16, 3), "dL_dopacity": (n,),
+              "dL_dscale": (n, 3), "dL_drot": (n, 4), "dL_dmean2D": (n, 3), "dL_dconic": (n, 4), "dL_dcov3D": (n, 6)}
+    g = {}
+    for key, shape in shapes.items():
+        t = out.get(key) if out else None
+        if t is None:
+            t = torch.empty(shape, dtype=f32, device=dev)
+        else:
+            numel = 1
+            for d in shape:
+                numel *= d
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == f32 and t.is_contiguous()
+                    and t.numel() == numel):
+                raise ValueError(f"out[{key!r}] must be a contiguous float32 CUDA tensor with {numel} elements")
+        g[key] = t
     p = _lib.ptr
     rc = _lib.lib().gsb_backward(ctx.h, _lib.stream_ptr(ctx.device_index), C.byref(frame), n, p(means), p(opac), p(sh),
                                  p(scl), p(rot), p(radii_t), p(xy), p(con_o), p(colors), p(clamped_state), p(cov3),

@@ -384,22 +384,22 @@ def ours(args):
                 ready.record(copy_stream)
             main.wait_event(ready)
             loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0)
-            g = gb.backward(**scene.backward_kwargs(P.as_dict(), cam, buf, dpix, background=bg))
             if world > 1:
-                flat = torch.cat([g["dL_dmean3D"].reshape(-1), g["dL_dscale"].reshape(-1), g["dL_drot"].reshape(-1),
-                                  g["dL_dopacity"].reshape(-1), g["dL_dshs"].reshape(-1)])
-                dist.all_reduce(flat)
-                o = 0
-                for key, numel in (("dL_dmean3D", 3 * n), ("dL_dscale", 3 * n), ("dL_drot", 4 * n), ("dL_dopacity", n),
-                                   ("dL_dshs", 48 * n)):
-                    g[key] = flat[o:o + numel]
-                    o += numel
-            lr = T.learning_rates(it)
-            gopt.adam_update(g["dL_dmean3D"], g["dL_dscale"], g["dL_drot"], g["dL_dopacity"], g["dL_dshs"], n,
-                             lr["lr_pos"], lr["lr_scale"], lr["lr_rot"], lr["lr_opac"], lr["lr_sh"], 0.9, 0.999, 1e-8, it,
-                             P["positions"], P["scales"], P["rotations"], P["opacities"], P["shs"],
-                             M["positions"], M["scales"], M["rotations"], M["opacities"], M["shs"],
-                             V["positions"], V["scales"], V["rotations"], V["opacities"], V["shs"])
+                # multi-GPU: the gradients land directly in the symmetric flat buffer (backward's `out`),
+                # and the public exchange step (fused NVLink reduction + Adam + parameter broadcast, or
+                # NCCL all-reduce + Adam) replaces adam_update -- the reference has no multi-GPU API
+                gb.backward(**scene.backward_kwargs(P.as_dict(), cam, buf, dpix, background=bg),
+                            out={"dL_dmean3D": G["positions"], "dL_dscale": G["scales"], "dL_drot": G["rotations"],
+                                 "dL_dopacity": G["opacities"], "dL_dshs": G["shs"]})
+                T.exchange_and_step(it)
+            else:
+                g = gb.backward(**scene.backward_kwargs(P.as_dict(), cam, buf, dpix, background=bg))
+                lr = T.learning_rates(it)
+                gopt.adam_update(g["dL_dmean3D"], g["dL_dscale"], g["dL_drot"], g["dL_dopacity"], g["dL_dshs"], n,
+                                 lr["lr_pos"], lr["lr_scale"], lr["lr_rot"], lr["lr_opac"], lr["lr_sh"], 0.9, 0.999, 1e-8,
+                                 it, P["positions"], P["scales"], P["rotations"], P["opacities"], P["shs"],
+                                 M["positions"], M["scales"], M["rotations"], M["opacities"], M["shs"],
+                                 V["positions"], V["scales"], V["rotations"], V["opacities"], V["shs"])
             # D2H of the step's result, every step, into pinned memory; the host consumes the value one
             # step later (after the next forward call), so preparing the next step overlaps this step's
             # Adam instead of waiting for it.  All K values are read before the clock stops.
@@ -432,7 +432,9 @@ def ours(args):
         barrier()
         e2e = {"value": K * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(h * w * 3 * 4 + 2 * 64 + 24),
                "d2h_bytes_per_step": 8 + 8, "ms_per_step": dt / K * 1e3,
-               "api": "forward.render_gaussians + loss.l1_loss_and_gradients + backward.backward + optimizer.adam_update",
+               "api": ("forward.render_gaussians + loss.l1_loss_and_gradients + backward.backward + optimizer.adam_update"
+                       if world == 1 else "forward.render_gaussians + loss.l1_loss_and_gradients + backward.backward(out="
+                       "flat gradient buffer) + Trainer.exchange_and_step"),
                "loss_readback": "D2H into pinned memory every step, consumed by the host one step later; all K read "
                                 "inside the timed region", "last_loss": losses[-1]}
 

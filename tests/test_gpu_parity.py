@@ -156,6 +156,24 @@ def test_backward_reduction_modes_agree_with_oracle(gs, oracle, mode, hand_masks
         _lib.context().set_option("bwd_reduce", 2)
 
 
+def test_backward_writes_into_caller_buffers(gs):
+    """backward(out=...) (our extension): results land in the given tensors, the others are allocated."""
+    params, cam, target = gs.scene.synthetic_scene(3000, 96, 64, 0.01, 0.1, seed=3)
+    img, _d, buf = gs.forward.render_gaussians(**gs.scene.render_kwargs(params, cam))
+    dpix = torch.from_numpy(np.random.default_rng(1).normal(size=(64, 96, 3)).astype(np.float32)).cuda()
+    kw = gs.scene.backward_kwargs(params, cam, buf, dpix)
+    ref = gs.backward.backward(**kw)
+    flat = torch.full((3000 * 51 + 16,), 7.0, device="cuda")
+    out = {"dL_dmean3D": flat[:9000].view(3000, 3), "dL_dshs": flat[9000:9000 + 144000].view(48000, 3)}
+    got = gs.backward.backward(**kw, out=out)
+    assert got["dL_dmean3D"].data_ptr() == flat.data_ptr() and got["dL_dshs"].data_ptr() == flat[9000:].data_ptr()
+    assert bool((flat[153000:] == 7.0).all())                      # nothing written past the views
+    for k in ("dL_dmean3D", "dL_dshs", "dL_dscale", "dL_drot"):       # these four do not depend on atomics' order
+        assert torch.equal(got[k], ref[k]) or torch.allclose(got[k], ref[k], rtol=1e-4, atol=1e-9), k
+    with pytest.raises(ValueError):
+        gs.backward.backward(**kw, out={"dL_dscale": torch.empty(5, device="cuda")})
+
+
 def test_nothing_visible_gives_zero_image(gs, oracle):
     """forward.py:830: when no Gaussian is rendered the image is all ZEROS, not background."""
     params, cam, _ = gs.scene.synthetic_scene(500, 64, 48, 0.01, 0.05)

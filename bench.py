@@ -319,25 +319,30 @@ def ours(args):
         sampler.start()
     launches0 = T.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    T.exchange_events = []
     e0.record()
     for it in range(W, W + K):
         T.train_step(it, batch(it), densify=False)
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = T.ctx.launches - launches0
+    value = K * world / (ms_total * 1e-3)
+
+    # ---- where the exchange + Adam part of the step goes (10 extra, untimed steps with CUDA events) -----
     # device time this rank spends between the end of its backward and the end of the exchange + Adam
     # (incl. waiting for the slowest rank at the first barrier); max over ranks of the per-step mean
+    T.exchange_events, T.exchange_parts = [], []
+    for it in range(W + K, W + K + 10):
+        T.train_step(it, batch(it), densify=False)
+    barrier()
     exchange_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in T.exchange_events])))
     parts = None
     if T.exchange_parts:
-        arr = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in T.exchange_parts[-K:]]).mean(axis=0)
+        arr = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in T.exchange_parts]).mean(axis=0)
         parts = {"wait_and_barrier_ms": round(max_over_ranks(float(arr[0])), 4),
                  "fused_kernel_ms": round(max_over_ranks(float(arr[1])), 4),
                  "final_barrier_ms": round(max_over_ranks(float(arr[2])), 4)}
     T.exchange_events = None
-    launches = T.ctx.launches - launches0
-    value = K * world / (ms_total * 1e-3)
 
     # ---- pure forward+backward of the single-view headline (camera 0) ---------------------------
     tgt0 = T.targets[0]

@@ -53,6 +53,7 @@ _SIGS = {
     "gsb_adam_step_peers": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64,
                                       C.c_uint64, vp, vp] + [f32] * 8 + [i32]),
     "gsb_fill_f32": (C.c_int, [vp, vp, vp, i64, f32]),
+    "gsb_selftest_block_mask": (C.c_int, [vp, vp, i32, vp, vp, vp]),
     "gsb_selftest_div": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
     "gsb_accumulate_f32": (C.c_int, [vp, vp, vp, vp, i64]),
     "gsb_init_gaussian_params": (C.c_int, [vp, vp, i32, f32] + [vp] * 5),

@@ -165,6 +165,41 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
 
 }  // namespace
 
+// Diagnostic: for each test case (one Gaussian against one tile) the culling mask of gs_block_mask and
+// the exact set of pixels the forward would blend it into if nothing else had been drawn (power <= 0 and
+// alpha >= 1/255 with the contract's arithmetic).  The mask must cover that set: tests/test_gpu_parity.py.
+namespace {
+__global__ void selftest_block_mask_kernel(int n, const float* __restrict__ g /* n x 8: gx gy a b c opacity x0 y0 */,
+                                           unsigned* __restrict__ mask, unsigned* __restrict__ active /* n x 8 */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gx = g[8 * i + 0], gy = g[8 * i + 1], ca = g[8 * i + 2], cb = g[8 * i + 3], cc = g[8 * i + 4];
+  const float o = g[8 * i + 5], x0 = g[8 * i + 6], y0 = g[8 * i + 7];
+  mask[i] = gs_block_mask(gx, gy, ca, cb, cc, gs_power_threshold(o), x0, y0);
+  for (int w = 0; w < 8; ++w) {
+    unsigned bits = 0u;
+    for (int b = 0; b < 32; ++b) {
+      const int p = 32 * w + b, r = p >> 4, c = p & 15;
+      const float dx = gx - (x0 + (float)c), dy = gy - (y0 + (float)r);
+      const float power = gs_power(ca, cb, cc, dx, dy);
+      if (power > 0.0f) continue;
+      const float alpha = f_min(0.99f, o * gs_expf(power));
+      if (alpha < (1.0f / 255.0f)) continue;
+      bits |= 1u << b;   // NaN power / alpha fall through to here, like in the tile kernels
+    }
+    active[8 * i + w] = bits;
+  }
+}
+}  // namespace
+
+GSB_API int gsb_selftest_block_mask(gsb_ctx* ctx, gsb_stream s, int32_t count, const float* cases, uint32_t* mask,
+                                    uint32_t* active) {
+  if (!ctx) return GSB_ERR_INVALID;
+  if (count <= 0) return GSB_OK;
+  GSB_LAUNCH(ctx, selftest_block_mask_kernel, (count + 127) / 128, 128, 0, (cudaStream_t)s, count, cases, mask, active);
+  return GSB_OK;
+}
+
 GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* rgb,
                               const float* conic_opacity, const float* depths, float* image, float* inv_depth,

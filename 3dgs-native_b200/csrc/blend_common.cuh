@@ -38,6 +38,9 @@ __device__ __forceinline__ float gs_sqrt_approx(float x) {  // MUFU.SQRT, ~1 ulp
 // function gives the same value in translation units built with and without -fmad.
 __device__ __forceinline__ unsigned gs_block_mask(float gx, float gy, float ca, float cb, float cc, float thr,
                                                   float x0, float y0) {
+  // a non-finite centre or conic makes NaN exponents, which pass both of the reference's tests (and
+  // poison the pixel there): never culled, whatever the opacity
+  if (!(fabsf((gx + gy) + (ca + cb) + cc) < 3.0e38f)) return 0xffffffffu;
   if (thr == __int_as_float(0x7f800000)) return 0u;  // opacity < 1/255: alpha can never reach 1/255
   if (!(ca > 0.0f)) return 0xffffffffu;
   const float t2 = __fmaf_rn(-2.0f * thr, 1.0001f, 1e-3f);

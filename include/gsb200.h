@@ -212,6 +212,14 @@ int gsb_adam_step_peers(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, in
 /* replaces zero_gradients (train.py:94-115) -- and any other "fill float" need */
 int gsb_fill_f32(gsb_ctx* ctx, gsb_stream s, float* dst, int64_t count, float value);
 
+/* Diagnostic (no reference counterpart): the tile kernels skip a (Gaussian, 8-pixel half row) when a
+ * conservative ellipse / row test says no pixel of it can reach alpha >= 1/255.  cases: count x 8 floats
+ * (gx, gy, conic a, b, c, opacity, tile x0, y0); mask[i] = the 32-bit mask (bit 2r + h: row r, half h);
+ * active[i][8] = the 256 pixels (bit 16r + x) that do pass power <= 0 and alpha >= 1/255 under the
+ * arithmetic contract.  Every active pixel must be covered by a mask bit. */
+int gsb_selftest_block_mask(gsb_ctx* ctx, gsb_stream s, int32_t count, const float* cases, uint32_t* mask,
+                            uint32_t* active);
+
 /* Diagnostic (no reference counterpart): the Adam kernels divide with a rescaled fast path instead of
  * the compiler's range-checked `/`; out_fast[i] = that division of a[i] by b[i] (b > 0), out_const[i]
  * = the variant for host-known divisors (reciprocal passed in), out_ref[i] = a[i] / b[i].  The three

@@ -27,6 +27,10 @@ def gs():
     return types.SimpleNamespace(forward=forward, backward=backward, scene=scene)
 
 
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
 def _np(t):
     return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
 
@@ -172,6 +176,55 @@ def test_backward_writes_into_caller_buffers(gs):
         assert torch.equal(got[k], ref[k]) or torch.allclose(got[k], ref[k], rtol=1e-4, atol=1e-9), k
     with pytest.raises(ValueError):
         gs.backward.backward(**kw, out={"dL_dscale": torch.empty(5, device="cuda")})
+
+
+def test_culling_mask_covers_every_contributing_pixel(gs):
+    """Property test of gs_block_mask, the conservative ellipse / half-row test both tile kernels cull with:
+    for random conics (isotropic to needle-like, sub-pixel to thousands of pixels), centres inside, next
+    to and far from the tile, every opacity regime and degenerate inputs, each pixel that passes the
+    forward's own tests (power <= 0, alpha >= 1/255, contract arithmetic) must lie in a kept half row."""
+    from gsb200 import _lib
+    ctx = _lib.context()
+    rng = np.random.default_rng(123)
+    n = 400_000
+    # covariance = R diag(s1^2, s2^2) R^T + 0.3 I  -> conic (what preprocess produces), plus raw extremes
+    s1 = np.exp(rng.uniform(np.log(0.05), np.log(3000.0), n))
+    s2 = s1 * np.exp(rng.uniform(np.log(1e-3), 0.0, n))
+    th = rng.uniform(0, np.pi, n)
+    c, s = np.cos(th), np.sin(th)
+    xx = c * c * s1 * s1 + s * s * s2 * s2 + 0.3
+    yy = s * s * s1 * s1 + c * c * s2 * s2 + 0.3
+    xy = c * s * (s1 * s1 - s2 * s2)
+    det = xx * yy - xy * xy
+    ca, cb, cc = yy / det, -xy / det, xx / det
+    x0 = 16.0 * rng.integers(0, 240, n)
+    y0 = 16.0 * rng.integers(0, 135, n)
+    reach = 3.5 * s1 + 24.0
+    gx = x0 + 8.0 + rng.uniform(-1, 1, n) * reach * rng.choice([0.05, 0.5, 1.0, 1.5], n)
+    gy = y0 + 8.0 + rng.uniform(-1, 1, n) * reach * rng.choice([0.05, 0.5, 1.0, 1.5], n)
+    op = rng.choice([1.0, 0.99, 0.5, 0.05, 0.0040, 1.0 / 255.0, 0.00393, 0.0, 2.0], n)
+    op = np.where(rng.uniform(0, 1, n) < 0.5, rng.uniform(0, 1, n), op)
+    cases = np.stack([gx, gy, ca, cb, cc, op, x0, y0], axis=1).astype(np.float32)
+    # degenerate / hostile inputs: must never crash and must stay conservative
+    cases[:64, 2] = np.repeat(np.array([0.0, -1.0, np.nan, np.inf, 1e-30, 1e30, 3.3, 1e-12], dtype=np.float32), 8)
+    cases[64:96, 3] = np.float32(np.nan)
+    cases[96:128, 5] = np.float32(np.nan)
+    cases[128:160, 0] = np.repeat(np.array([1e7, -1e7, np.inf, np.nan], dtype=np.float32), 8)
+    tc = _cuda(cases)
+    mask = torch.empty(n, dtype=torch.int32, device="cuda")
+    active = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+    ctx.check(_lib.lib().gsb_selftest_block_mask(ctx.h, _lib.stream_ptr(ctx.device_index), n, _lib.ptr(tc),
+                                                 _lib.ptr(mask), _lib.ptr(active)))
+    torch.cuda.synchronize()
+    m = mask.cpu().numpy().view(np.uint32)
+    a = active.cpu().numpy().view(np.uint32)
+    act = ((a[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(n, 16, 2, 8).any(axis=3)  # [n, row, half]
+    kept = ((m[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(n, 16, 2).astype(bool)
+    missed = act & ~kept
+    assert not missed.any(), f"{missed.any(axis=(1, 2)).sum()} cases lose a contributing half row, e.g. {cases[missed.any(axis=(1, 2))][:3]}"
+    # and the test is worth its cost: a good part of the half rows without any contributing pixel is culled
+    empty = ~act
+    assert kept[empty].mean() < 0.5, kept[empty].mean()
 
 
 def test_nothing_visible_gives_zero_image(gs, oracle):

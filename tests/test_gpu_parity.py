@@ -172,8 +172,9 @@ def test_backward_writes_into_caller_buffers(gs):
     got = gs.backward.backward(**kw, out=out)
     assert got["dL_dmean3D"].data_ptr() == flat.data_ptr() and got["dL_dshs"].data_ptr() == flat[9000:].data_ptr()
     assert bool((flat[153000:] == 7.0).all())                      # nothing written past the views
-    for k in ("dL_dmean3D", "dL_dshs", "dL_dscale", "dL_drot"):       # these four do not depend on atomics' order
-        assert torch.equal(got[k], ref[k]) or torch.allclose(got[k], ref[k], rtol=1e-4, atol=1e-9), k
+    for k in ref:                           # two runs differ by the order of the atomics only
+        a, b = got[k].double(), ref[k].double()
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12, k
     with pytest.raises(ValueError):
         gs.backward.backward(**kw, out={"dL_dscale": torch.empty(5, device="cuda")})
 

@@ -109,12 +109,14 @@ GSB_API int gsb_create(gsb_ctx** out, int device) {
   if (cudaMalloc((void**)&ctx->d_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->sort_small, (256 + 16) * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_accum, 2 * sizeof(double)) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_count, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return GSB_ERR_NOMEM;
   }
   cudaMemset(ctx->d_scalars, 0, 16 * sizeof(int32_t));
   cudaMemset(ctx->sort_small, 0, (256 + 16) * sizeof(uint32_t));
+  cudaMemset(ctx->d_accum, 0, 2 * sizeof(double));
   memset(ctx->h_scalars, 0, 16 * sizeof(int32_t));
   *out = ctx;
   return GSB_OK;
@@ -125,7 +127,7 @@ GSB_API int gsb_destroy(gsb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   void* bufs[] = {ctx->keys_a, ctx->keys_b, ctx->vals_a, ctx->vals_b, ctx->sort_table, ctx->sort_small, ctx->scan_sums,
-                  ctx->tiles_touched, ctx->dcov3d, ctx->d_scalars, ctx->tile_count};
+                  ctx->tiles_touched, ctx->dcov3d, ctx->d_scalars, ctx->tile_count, ctx->d_accum};
   for (void* p : bufs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);

@@ -42,6 +42,8 @@ struct gsb_ctx {
   // tile-binning scratch: [num_tiles] counts + [num_tiles] write cursors
   int32_t* tile_count = nullptr;
   int64_t tile_cap = 0;
+  int64_t tile_clean = 0;  // leading ints of tile_count (and the rank cursor) known to be zero: tile_scan_kernel
+                           // re-zeroes what the counting pass touched, so a steady-state frame needs no memset
   // per-Gaussian internal buffers for gsb_forward / gsb_backward
   int32_t* tiles_touched = nullptr;
   float* dcov3d = nullptr;
@@ -51,6 +53,7 @@ struct gsb_ctx {
   // device + pinned host scalars
   int32_t* d_scalars = nullptr;  // [16]
   int32_t* h_scalars = nullptr;  // pinned [16]
+  double* d_accum = nullptr;     // [2] loss accumulator + CTA ticket (8 bytes); self-resetting, see l1_loss_grad_kernel
 };
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...);

@@ -49,9 +49,11 @@ tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ 
 
 // Single CTA: exclusive scan over the tiles.  Writes ranges (start,end) -- (0,0) for empty tiles,
 // like the zero-initialised reference buffer --, the per-tile write cursors, the total and the max.
+// It is the last reader of the counters and of the rank cursor, so it leaves both zeroed for the next
+// frame (gsb_tile_binning_prepare then skips its two memsets).
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __restrict__ ranges,
-                 int* __restrict__ out_total_max) {
+tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__ ranges,
+                 int* __restrict__ out_total_max, int* __restrict__ cursor) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_max[32];
@@ -62,6 +64,7 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
   for (int base = 0; base < num_tiles; base += 1024) {
     const int i = base + tid;
     const int c = (i < num_tiles) ? tile_count[(size_t)i * kCntStride] : 0;
+    if (c != 0) tile_count[(size_t)i * kCntStride] = 0;
     my_max = max(my_max, c);
     int inc = c;
 #pragma unroll
@@ -94,6 +97,7 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
     for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
     out_total_max[0] = s_carry;
     out_total_max[1] = m;
+    *cursor = 0;
   }
 }
 
@@ -364,20 +368,28 @@ tile_radix_kernel(const int2* __restrict__ ranges, const unsigned long long* __r
 // ---- host side -------------------------------------------------------------------------------
 // prepare: size and zero the per-tile counters (and the rank cursor of the fused counting pass)
 int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles) {
-  int rc = gsb_grow(ctx, (void**)&ctx->tile_count, &ctx->tile_cap, (int64_t)num_tiles * kCntStride, sizeof(int32_t), s);
+  const int64_t need = (int64_t)num_tiles * kCntStride, old_cap = ctx->tile_cap;
+  int rc = gsb_grow(ctx, (void**)&ctx->tile_count, &ctx->tile_cap, need, sizeof(int32_t), s);
   if (rc != GSB_OK) return rc;
+  if (ctx->tile_cap != old_cap) ctx->tile_clean = 0;  // reallocated: contents unknown
   // The arrival ranks live in vals_a (one int per duplicate).  Its capacity is a guess until D is
   // known (previous frame's D); if it turns out too small the caller re-runs the counting pass.
   if (ctx->bin_cap == 0 && (rc = gsb_reserve_binning(ctx, s, 4 * (int64_t)n + 1024)) != GSB_OK) return rc;
-  GSB_CUDA(ctx, cudaMemsetAsync(ctx->tile_count, 0, sizeof(int32_t) * (size_t)num_tiles * kCntStride, s));
-  GSB_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars + 8, 0, sizeof(int32_t), s));
+  // The previous frame's tile_scan_kernel left the counters and the cursor zeroed (tile_clean); only the
+  // first frame, a larger tile grid, or a frame that failed between here and its scan pays the memsets.
+  if (ctx->tile_clean < need) {
+    GSB_CUDA(ctx, cudaMemsetAsync(ctx->tile_count, 0, sizeof(int32_t) * (size_t)need, s));
+    GSB_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars + 8, 0, sizeof(int32_t), s));
+  }
+  ctx->tile_clean = 0;  // dirty from here until the scan has been queued
   return GSB_OK;
 }
 
 // scan the counters into ranges, start the read-back of (D, max count) and mark it with an event
 int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges) {
   GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
-             ctx->d_scalars + 4);
+             ctx->d_scalars + 4, ctx->d_scalars + 8);
+  ctx->tile_clean = (int64_t)num_tiles * kCntStride;
   GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
   return GSB_OK;

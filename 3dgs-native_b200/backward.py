@@ -12,7 +12,7 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
              scale_modifier=1.0, viewmatrix=None, projmatrix=None, tan_fovx=0.5, tan_fovy=0.5,
              image_height=256, image_width=256, campos=None, radii=None, means2D=None, conic_opacity=None,
              rgb=None, clamped=None, cov3Ds=None, geom_buffer=None, binning_buffer=None, img_buffer=None,
-             degree=3, debug=False, out=None):
+             degree=3, debug=False, out=None, sh_compact=False):
     """Gradients of all Gaussian parameters.  Same arguments and the same 9-key result dict as the
     reference.  Like there, ``img_buffer`` (ranges, final_Ts, n_contrib) and ``binning_buffer``
     (point_list) are required, ``scale_modifier`` is accepted but not used by the covariance
@@ -22,7 +22,11 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
     ``out`` (not a reference argument; default None = allocate like the reference does): a dict with
     any of the nine result keys mapping to preallocated contiguous float32 CUDA tensors of the right
     size, which then receive those results -- e.g. views of a flat gradient buffer that a multi-GPU
-    exchange reads in place."""
+    exchange reads in place.
+    ``sh_compact`` (not a reference argument; default False): ``dL_dshs`` then holds the two rank-1
+    factors of the SH gradient in its first 8 n floats -- per Gaussian (dL_dRGB after the clamp mask,
+    unit view direction, 0, 0) -- instead of the 48 n products (gsb_backward_compact_sh); the rest of
+    the tensor is left untouched.  For ``Trainer.exchange_and_step(compact=True)``."""
     if img_buffer is None or binning_buffer is None:
         raise ValueError("backward() needs img_buffer{ranges,final_Ts,n_contrib} and binning_buffer{point_list} "
                          "(backward.py:1084-1090)")
@@ -78,7 +82,8 @@ def backward(background, means3D, dL_dpixels, opacity=None, shs=None, scales=Non
                 raise ValueError(f"out[{key!r}] must be a contiguous float32 CUDA tensor with {numel} elements")
         g[key] = t
     p = _lib.ptr
-    rc = _lib.lib().gsb_backward(ctx.h, _lib.stream_ptr(ctx.device_index), C.byref(frame), n, p(means), p(opac), p(sh),
+    fn = _lib.lib().gsb_backward_compact_sh if sh_compact else _lib.lib().gsb_backward
+    rc = fn(ctx.h, _lib.stream_ptr(ctx.device_index), C.byref(frame), n, p(means), p(opac), p(sh),
                                  p(scl), p(rot), p(radii_t), p(xy), p(con_o), p(colors), p(clamped_state), p(cov3),
                                  p(point_list), p(ranges), p(final_Ts), p(n_contrib), p(dpix), p(g["dL_dmean3D"]),
                                  p(g["dL_dcolor"]), p(g["dL_dshs"]), p(g["dL_dopacity"]), p(g["dL_dscale"]),

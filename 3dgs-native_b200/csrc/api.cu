@@ -160,7 +160,7 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
     g_tile_sort = value;
     return GSB_OK;
   }
-  if (!strcmp(name, "bwd_reduce") && value >= 0 && value <= 2) {
+  if (!strcmp(name, "bwd_reduce") && value >= 0 && value <= 4) {
     g_bwd_reduce = value;
     return GSB_OK;
   }
@@ -299,14 +299,14 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
                            final_T, n_contrib, block_masks);
 }
 
-GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
+static int backward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
                          const float* opacities, const float* shs, const float* scales, const float* rotations,
                          const int32_t* radii, const float* points_xy, const float* conic_opacity, const float* rgb,
                          const float* clamped_state, const float* cov3Ds, const int32_t* point_list,
                          const int32_t* ranges, const float* final_T, const int32_t* n_contrib,
                          const float* dL_dpixels, float* dL_dmean3D, float* dL_dcolor, float* dL_dshs,
                          float* dL_dopacity, float* dL_dscale, float* dL_drot, float* dL_dmean2D, float* dL_dconic,
-                         float* dL_dcov3D, const int32_t* block_masks) {
+                         float* dL_dcov3D, const int32_t* block_masks, int sh_compact) {
   (void)opacities;  // converted and unused by the reference as well (backward.py:1056)
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && n >= 0, "gsb_backward: bad frame or n");
@@ -319,10 +319,40 @@ GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_
                           dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, block_masks);
   if (rc != GSB_OK) return rc;
   // backward.py:1155-1182
-  rc = gsb_preprocess_backward(ctx, s_, f, n, means, radii, shs, scales, rotations, cov3Ds, clamped_state, dL_dmean2D,
-                               dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, dL_drot, nullptr);
+  rc = gsb_preprocess_backward_impl(ctx, s, f, n, means, radii, shs, scales, rotations, cov3Ds, clamped_state,
+                                    dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, dL_drot, nullptr,
+                                    sh_compact);
   if (rc != GSB_OK) return rc;
   // backward.py:1119,1195: the returned dL_dcov3D is a fresh zero buffer no kernel writes
   if (dL_dcov3D) GSB_CUDA(ctx, cudaMemsetAsync(dL_dcov3D, 0, sizeof(float) * 6 * (size_t)n, s));
   return GSB_OK;
+}
+
+GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
+                         const float* opacities, const float* shs, const float* scales, const float* rotations,
+                         const int32_t* radii, const float* points_xy, const float* conic_opacity, const float* rgb,
+                         const float* clamped_state, const float* cov3Ds, const int32_t* point_list,
+                         const int32_t* ranges, const float* final_T, const int32_t* n_contrib,
+                         const float* dL_dpixels, float* dL_dmean3D, float* dL_dcolor, float* dL_dshs,
+                         float* dL_dopacity, float* dL_dscale, float* dL_drot, float* dL_dmean2D, float* dL_dconic,
+                         float* dL_dcov3D, const int32_t* block_masks) {
+  return backward_impl(ctx, s_, f, n, means, opacities, shs, scales, rotations, radii, points_xy, conic_opacity, rgb,
+                       clamped_state, cov3Ds, point_list, ranges, final_T, n_contrib, dL_dpixels, dL_dmean3D, dL_dcolor,
+                       dL_dshs, dL_dopacity, dL_dscale, dL_drot, dL_dmean2D, dL_dconic, dL_dcov3D, block_masks, 0);
+}
+
+// gsb_backward whose dL_dshs receives the COMPACT SH gradient: [8 n] floats, per Gaussian (dL_dRGB masked, unit view
+// direction, 0, 0) -- the two factors the reference's 48 values are the outer product of (dL_dshs[16 i + k] =
+// basis_k(direction) * dL_dRGB, backward.py:127-213).  Consumed by gsb_adam_step_peers_compact.
+GSB_API int gsb_backward_compact_sh(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,
+                         const float* opacities, const float* shs, const float* scales, const float* rotations,
+                         const int32_t* radii, const float* points_xy, const float* conic_opacity, const float* rgb,
+                         const float* clamped_state, const float* cov3Ds, const int32_t* point_list,
+                         const int32_t* ranges, const float* final_T, const int32_t* n_contrib,
+                         const float* dL_dpixels, float* dL_dmean3D, float* dL_dcolor, float* dL_dshs,
+                         float* dL_dopacity, float* dL_dscale, float* dL_drot, float* dL_dmean2D, float* dL_dconic,
+                         float* dL_dcov3D, const int32_t* block_masks) {
+  return backward_impl(ctx, s_, f, n, means, opacities, shs, scales, rotations, radii, points_xy, conic_opacity, rgb,
+                       clamped_state, cov3Ds, point_list, ranges, final_T, n_contrib, dL_dpixels, dL_dmean3D, dL_dcolor,
+                       dL_dshs, dL_dopacity, dL_dscale, dL_drot, dL_dmean2D, dL_dconic, dL_dcov3D, block_masks, 1);
 }

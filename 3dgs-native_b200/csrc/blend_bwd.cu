@@ -503,6 +503,281 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-autonomous replay (bwd_reduce = 3, 4).  The kernel above shares one staged batch between the
+// eight warps of a tile, which costs two CTA barriers per 256 list entries -- and the eight blocks of
+// a tile carry very different hit counts, so a fifth of all warp cycles sit behind BAR.SYNC.  Here a
+// warp owns its 4x8 block from start to end and never meets another warp:
+//   * it walks the tile's list back to front 32 entries at a time: lane l reads the culling mask and
+//     the Gaussian id of one entry (two coalesced loads, issued one chunk ahead), the lanes whose
+//     mask touches the block gather their Gaussian (issued one chunk ahead as well, held in
+//     registers while the previous chunk is replayed) and append it to a 64-slot per-warp ring;
+//   * the ring is replayed two hits at a time exactly like the staged batch above (an odd hit waits
+//     for the next chunk), the S / W tiles and the tensor-core flush are the same;
+//   * ring capacity: <= 15 replayed hits of the open MMA group (the flush reads their Gaussians) +
+//     1 waiting + 32 new = 48.
+// No __syncthreads anywhere, so the CTA is only a packing unit: WPC warps = WPC blocks of one tile.
+struct WarpRing {
+  float4 a[64];   // x, y, conic.a, conic.c
+  float4 b[64];   // conic.b, opacity, power threshold, position in the tile's list (int bits)
+  float4 c[64];   // r, g, b, gid (int bits)
+  float sw[2][kGrp][kSRow];
+};
+
+template <int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB)
+blend_backward_warp_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
+                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                           const float* __restrict__ rgb, const float* __restrict__ final_T,
+                           const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+                           float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
+                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
+                           const unsigned* __restrict__ block_masks) {
+  constexpr unsigned full = 0xffffffffu;
+  constexpr int BPT = 8 / WPC;  // CTAs per tile
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  WarpRing& sm = reinterpret_cast<WarpRing*>(smem_raw)[threadIdx.x >> 5];
+
+  const int tile_id = blockIdx.x / BPT;
+  const int wb = (blockIdx.x % BPT) * WPC + (threadIdx.x >> 5);  // this warp's block of the tile, 0..7
+  const int tile_x = tile_id % P.grid_x, tile_y = tile_id / P.grid_x;
+  const int bx0 = tile_x * kTile + (wb & 1) * 8, by0 = tile_y * kTile + (wb >> 1) * 4;  // block origin
+  const int px = bx0 + (lane & 7);
+  const int py = by0 + (lane >> 3);
+  const gs_f2 npxy = gs_pack2(-(float)px, -(float)py);
+  const int2 range = ranges[tile_id];
+  const unsigned my_mask = gs_warp_mask(wb);
+
+  const bool inside = (px < P.W && py < P.H);
+  const size_t pix = inside ? ((size_t)py * P.W + px) : 0;
+  const float T_final = inside ? final_T[pix] : 0.0f;
+  float T = T_final;
+  const int kept = inside ? min(range.y - range.x, n_contrib[pix]) : 0;  // backward.py:619
+  const int my_max = __reduce_max_sync(full, kept);
+  if (my_max == 0) return;  // nothing was blended into this block
+  const float dp0 = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
+  const float dp1 = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
+  const float dp2 = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
+  float gamma = T_final * gs_dot3(P.bg0, P.bg1, P.bg2, dp0, dp1, dp2);  // see blend_backward_mma_kernel
+
+  const int fg = lane >> 2, ft = lane & 3;
+  const float fr = (float)ft;
+  const float m0 = fg == 0 ? 1.0f : fg == 2 ? fr : fg == 5 ? fr * fr : 0.0f;
+  const float m1 = fg == 1 ? 1.0f : fg == 4 ? fr : 0.0f;
+  const float m2 = fg == 3 ? 1.0f : 0.0f;
+  const bool dp_row_ok = fg < 3 && (by0 + ft) < P.H;
+  const float* const dp_row = dL_dpixels + (dp_row_ok ? 3 * ((size_t)(by0 + ft) * P.W + bx0) + fg : 0);
+  const int dp_cols = dp_row_ok ? min(8, P.W - bx0) : 0;
+
+  const float ddelx_dx = 0.5f * (float)P.W;
+  const float ddely_dy = 0.5f * (float)P.H;
+  float* const tS = &sm.sw[0][0][0];
+  float* const tW = &sm.sw[1][0][0];
+  const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
+  const bool have = P.cull && block_masks != nullptr;   // the forward's masks were handed on
+  const bool need_mask = P.cull && !have;               // recompute them (same values)
+
+  int wr = 0, rd = 0;   // ring counters: appended / replayed hits (slot = counter & 63)
+  int gslot = 0;        // hits in the open MMA group
+  float* pS = tS + lane;
+
+  auto replay_hit = [&](const float G, const float alpha, const int j, float& sv, float& wv) {
+    const float4 c = sm.c[j];
+    const float inv_1ma = rcp_approx(1.0f - alpha);
+    T = T * inv_1ma;
+    wv = alpha * T;
+    const float dc = gs_dot3(c.x, c.y, c.z, dp0, dp1, dp2);
+    const float dL_dalpha = T * dc - gamma * inv_1ma;
+    gamma = fmaf(dc, wv, gamma);
+    sv = G * dL_dalpha;
+  };
+
+  // the open group's hits are the ring entries gbase .. gbase + count - 1
+  auto flush_group = [&](const int gbase, const int count) {
+    __syncwarp();
+    float dm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const float4 va = *reinterpret_cast<const float4*>(tS + fg * kSRow + 8 * ft + 4 * half);
+      const float4 vb = *reinterpret_cast<const float4*>(tS + (fg + 8) * kSRow + 8 * ft + 4 * half);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float ks = (float)(4 * half + e);
+        const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
+        const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
+        const float b0 = m0 + ks * (m1 + ks * m2);
+        mma_tf32_k4(dm, h0, h1, b0);
+        mma_tf32_k4(dm, a0 - h0, a1 - h1, b0);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const float4 va = *reinterpret_cast<const float4*>(tW + fg * kSRow + 8 * ft + 4 * half);
+      const float4 vb = *reinterpret_cast<const float4*>(tW + (fg + 8) * kSRow + 8 * ft + 4 * half);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * half + e;
+        const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
+        const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
+        const float dpv = (i < dp_cols) ? __ldg(dp_row + 3 * i) : 0.0f;
+        const float p0 = tf32_hi(dpv);
+        mma_tf32_k4(dc, h0, h1, p0);
+        mma_tf32_k4(dc, a0 - h0, a1 - h1, p0);
+        mma_tf32_k4(dc, h0, h1, dpv - p0);
+      }
+    }
+    __syncwarp();
+    *reinterpret_cast<float2*>(tS + fg * kDRow + 2 * ft) = make_float2(dm[0], dm[1]);
+    *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 2 * ft) = make_float2(dm[2], dm[3]);
+    if (ft < 2) {
+      *reinterpret_cast<float2*>(tS + fg * kDRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
+      *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
+    }
+    __syncwarp();
+    const float4 m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow);
+    const float2 m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kDRow + 4);
+    const float4 col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow + 8);
+    const unsigned nz = (__float_as_uint(m03.x) | __float_as_uint(m03.y) | __float_as_uint(m03.z) |
+                         __float_as_uint(m03.w) | __float_as_uint(m45.x) | __float_as_uint(m45.y) |
+                         __float_as_uint(col.x) | __float_as_uint(col.y) | __float_as_uint(col.z)) << 1;
+    if (lane < count && nz != 0u) {
+      const int je = (gbase + lane) & 63;
+      const float4 ga = sm.a[je];
+      const float4 gb = sm.b[je];
+      const int gid = __float_as_int(sm.c[je].w);
+      const float ux = ga.x - (float)bx0, uy = ga.y - (float)by0;
+      const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
+      const float Sdx = ux * S0 - Si;
+      const float Sdy = uy * S0 - Sr;
+      const float Sdxx = ux * (Sdx - Si) + Sii;
+      const float Sdxy = ux * Sdy - uy * Si + Sir;
+      const float Sdyy = uy * (Sdy - Sr) + Srr;
+      const float o = gb.y;
+      atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
+      atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
+      atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
+      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx);
+      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy);
+      atomicAdd(dL_dconic + 4 * (size_t)gid + 0, -0.5f * o * Sdxx);
+      atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * o * Sdxy);
+      atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * o * Sdyy);
+      atomicAdd(dL_dopacity + gid, S0);
+    }
+    __syncwarp();
+    gslot = 0;
+    pS = tS + lane;
+  };
+
+  // ---- the two-deep pipeline: (mask, id) of chunk k+2 and the Gaussians of chunk k+1 are in flight
+  // while chunk k is replayed.  Chunk with upper end `chi`: lane l looks at list position chi - 1 - l.
+  auto load_entry = [&](const int chi, unsigned& m, int& g) {
+    const int pos = chi - 1 - lane;
+    m = 0u;
+    g = 0;
+    if (pos >= 0) {
+      const int e = range.x + pos;
+      g = point_list[e];
+      m = have ? block_masks[e] : 0xffffffffu;
+    }
+  };
+  float2 gp = make_float2(0.0f, 0.0f);
+  float4 gco = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float gc0 = 0.0f, gc1 = 0.0f, gc2 = 0.0f;
+  bool cand = false;
+  auto gather = [&](const unsigned m, const int g) {
+    // with handed-on masks only the entries that touch this block are fetched; without them every
+    // entry is (its mask is computed from what was fetched)
+    cand = need_mask ? (m != 0u) : ((m & my_mask) != 0u);
+    if (cand) {
+      gp = xy[g];
+      gco = conic_opacity[g];
+      gc0 = rgb[3 * g + 0];
+      gc1 = rgb[3 * g + 1];
+      gc2 = rgb[3 * g + 2];
+    }
+  };
+
+  int hi = my_max;
+  unsigned m_cur, m_nxt;
+  int g_cur, g_nxt;
+  load_entry(hi, m_cur, g_cur);
+  load_entry(hi - 32, m_nxt, g_nxt);
+  gather(m_cur, g_cur);
+
+  while (hi > 0) {
+    // 1. append the fetched chunk's hits to the ring, in replay order (ascending lane)
+    {
+      bool hit = cand;
+      float thr = 0.0f;
+      if (cand) {
+        thr = gs_power_threshold(gco.w);
+        if (need_mask)
+          hit = (gs_block_mask(gp.x, gp.y, gco.x, gco.y, gco.z, thr, tile_x0, tile_y0) & my_mask) != 0u;
+      }
+      const unsigned bal = __ballot_sync(full, hit);
+      if (hit) {
+        const int slot = (wr + __popc(bal & ((1u << lane) - 1u))) & 63;
+        sm.a[slot] = make_float4(gp.x, gp.y, gco.x, gco.z);
+        sm.b[slot] = make_float4(gco.y, gco.w, thr, __int_as_float(hi - 1 - lane));
+        sm.c[slot] = make_float4(gc0, gc1, gc2, __int_as_float(g_cur));
+      }
+      wr += __popc(bal);
+    }
+    // 2. advance the pipeline
+    hi -= 32;
+    m_cur = m_nxt;
+    g_cur = g_nxt;
+    cand = false;
+    if (hi > 0) {
+      gather(m_cur, g_cur);
+      load_entry(hi - 32, m_nxt, g_nxt);
+    }
+    __syncwarp();
+    // 3. replay what the ring holds, two hits per iteration; an odd hit waits for the next chunk
+    while (wr - rd >= 2) {
+      const int jA = rd & 63, jB = (rd + 1) & 63;
+      const float4 aA = sm.a[jA], bA = sm.b[jA];
+      const float4 aB = sm.a[jB], bB = sm.b[jB];
+      const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);
+      const float pwB = gs_power_packed(gs_pack2(aB.x, aB.y), npxy, gs_pack2(aB.z, aB.w), bB.x);
+      const bool actA = __float_as_int(bA.w) < kept && !(pwA > 0.0f) && !(pwA < bA.z);
+      const bool actB = __float_as_int(bB.w) < kept && !(pwB > 0.0f) && !(pwB < bB.z);
+      float svA = 0.0f, wvA = 0.0f, svB = 0.0f, wvB = 0.0f;
+      if (actA || actB) {
+        const float GA = exp_approx(pwA), GB = exp_approx(pwB);
+        const float alphaA = f_min(0.99f, bA.y * GA), alphaB = f_min(0.99f, bB.y * GB);
+        if (actA && !(alphaA < (1.0f / 255.0f))) replay_hit(GA, alphaA, jA, svA, wvA);
+        if (actB && !(alphaB < (1.0f / 255.0f))) replay_hit(GB, alphaB, jB, svB, wvB);
+      }
+      pS[0] = svA;
+      pS[kGrp * kSRow] = wvA;
+      pS[kSRow] = svB;
+      pS[kGrp * kSRow + kSRow] = wvB;
+      gslot += 2;
+      pS += 2 * kSRow;
+      rd += 2;
+      if (gslot == kGrp) flush_group(rd - kGrp, kGrp);
+    }
+  }
+  if (rd < wr) {  // the list's last hit
+    const int j = rd & 63;
+    const float4 a = sm.a[j], b4 = sm.b[j];
+    const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
+    float sv = 0.0f, wv = 0.0f;
+    if (__float_as_int(b4.w) < kept && !(power > 0.0f) && !(power < b4.z)) {
+      const float G = exp_approx(power);
+      const float alpha = f_min(0.99f, b4.y * G);
+      if (!(alpha < (1.0f / 255.0f))) replay_hit(G, alpha, j, sv, wv);
+    }
+    pS[0] = sv;
+    pS[kGrp * kSRow] = wv;
+    ++gslot;
+    ++rd;
+  }
+  if (gslot > 0) flush_group(rd - gslot, gslot);
+}
+
 // The four accumulation targets of the tile kernel zeroed by ONE launch (four memsets were four stream
 // operations of ~2 us each in front of a 0.3 ms kernel).  16-byte stores over each array's aligned body.
 struct ZeroJob {
@@ -557,6 +832,26 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
     return GSB_OK;
   }
   bool& attr_set = ctx->smem_optin_blend_bwd;  // > 48 KB of dynamic shared memory needs the opt-in (per device)
+  if (g_bwd_reduce >= 3) {  // warp-autonomous replay: 3 = four warps per CTA (seven CTAs per SM), 4 = eight (three)
+    const long long tiles = (long long)grid.x * grid.y;
+    if (g_bwd_reduce == 3) {
+      GSB_LAUNCH(ctx, (blend_backward_warp_kernel<4, 7>), (unsigned)(tiles * 2), 128, 4 * sizeof(WarpRing), s, P,
+                 reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
+                 reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
+                 dL_dconic, dL_dopacity, dL_dcolor, masks);
+    } else {
+      if (!ctx->smem_optin_blend_bwd_w8) {
+        GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_warp_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(8 * sizeof(WarpRing))));
+        ctx->smem_optin_blend_bwd_w8 = true;
+      }
+      GSB_LAUNCH(ctx, (blend_backward_warp_kernel<8, 3>), (unsigned)tiles, 256, 8 * sizeof(WarpRing), s, P,
+                 reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
+                 reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
+                 dL_dconic, dL_dopacity, dL_dcolor, masks);
+    }
+    return GSB_OK;
+  }
   if (!attr_set) {
     GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(BwdSmem)));

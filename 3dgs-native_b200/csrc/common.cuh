@@ -24,7 +24,7 @@ struct gsb_ctx {
   char err[512] = {0};
   int64_t launches = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: done once per context, not per process
-  bool smem_optin_blend_bwd = false, smem_optin_radix = false, smem_optin_tilesort = false;
+  bool smem_optin_blend_bwd = false, smem_optin_blend_bwd_w8 = false, smem_optin_radix = false, smem_optin_tilesort = false;
 
   // binning scratch (grow-only): sort double buffers
   int64_t* keys_a = nullptr;
@@ -256,6 +256,38 @@ __device__ __forceinline__ float gs_dot3(float a0, float a1, float a2, float b0,
 #define GS_C3_5 1.445305721320277f
 #define GS_C3_6 (-0.5900435899266435f)
 
+// The 16 real SH basis values of sh_backward_kernel (backward.py:127-213) at the unit direction
+// (x, y, z), zero above `deg`: dL_dshs[16 i + k] = basis[k] * dL_dRGB.  One definition for the two places
+// that evaluate it (preprocess_bwd.cu and the compact SH-gradient exchange in optimizer.cu), so both
+// produce the same bits.
+__device__ __forceinline__ void gs_sh_basis(const int deg, const float x, const float y, const float z, float basis[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) basis[k] = 0.0f;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  basis[0] = GS_SH_C0;
+  if (deg > 0) {
+    basis[1] = -GS_SH_C1 * y;
+    basis[2] = GS_SH_C1 * z;
+    basis[3] = -GS_SH_C1 * x;
+    if (deg > 1) {
+      basis[4] = GS_C2_0 * xy;
+      basis[5] = GS_C2_1 * yz;
+      basis[6] = GS_C2_2 * (2.0f * zz - xx - yy);
+      basis[7] = GS_C2_3 * xz;
+      basis[8] = GS_C2_4 * (xx - yy);
+      if (deg > 2) {
+        basis[9] = GS_C3_0 * y * (3.0f * xx - yy);
+        basis[10] = GS_C3_1 * xy * z;
+        basis[11] = GS_C3_2 * y * (4.0f * zz - xx - yy);
+        basis[12] = GS_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+        basis[13] = GS_C3_4 * x * (4.0f * zz - xx - yy);
+        basis[14] = GS_C3_5 * z * (xx - yy);
+        basis[15] = GS_C3_6 * x * (xx - 3.0f * yy);
+      }
+    }
+  }
+}
+
 // Per-view constants in kernel-parameter space
 struct FrameK {
   float view[16];
@@ -286,6 +318,14 @@ int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_
                         const float* scales, const float* rotations, const float* opacities, const float* shs,
                         int32_t* radii, float* points_xy, float* depths, float* cov3Ds, float* rgb,
                         float* conic_opacity, int32_t* tiles_touched, float* clamped_state, const PreBin* bin);
+
+// gsb_preprocess_backward with the choice of SH-gradient output: the full [48 n] array, or (sh_compact
+// = 1) the rank-1 factors it is the outer product of, [8 n]: (dL_dRGB masked, unit direction, 0, 0).
+int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
+                                 const int32_t* radii, const float* shs, const float* scales, const float* rotations,
+                                 const float* cov3Ds, const float* clamped_state, const float* dL_dmean2D,
+                                 const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D, float* dL_dshs,
+                                 float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact);
 
 // ---- stage launchers implemented across the .cu files (host side) --------------------------
 int gsb_scan_i32(gsb_ctx* ctx, cudaStream_t s, int64_t n, const int32_t* in, int32_t* out, bool exclusive,

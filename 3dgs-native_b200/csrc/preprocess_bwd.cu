@@ -20,6 +20,11 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kShStride = 49;
 
+// COMPACT: instead of the 48 SH gradients the kernel stores the two factors of that rank-1 product --
+// (dL_dRGB masked, unit view direction) as two float4 per Gaussian at dL_dshs[8 i] -- for the
+// multi-GPU exchange, which ships 32 bytes per Gaussian and view instead of 192 and expands them on
+// the receiving side with the same gs_sh_basis.
+template <bool COMPACT>
 __global__ void __launch_bounds__(kThreads, 6)
 preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict__ means, const int* __restrict__ radii,
                            const float* __restrict__ shs, const float* __restrict__ scales,
@@ -78,6 +83,7 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
     float4 o_rot = make_float4(0.f, 0.f, 0.f, 0.f);
     float o_dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool sh_written = false;
+    float4 shc0 = make_float4(0.f, 0.f, 0.f, 0.f), shc1 = shc0;  // COMPACT: zeros for a skipped Gaussian
 
     if (in_radius > 0) {
       // ================= compute_cov2d_backward_kernel, backward.py:258-435 =================
@@ -200,15 +206,10 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
             dRGB[c] = in_dcol[c] * (1.0f + (-1.0f * in_cl[c]));
           float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
           float basis[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) basis[k] = 0.0f;
           const int deg = f.degree;
           const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-          basis[0] = GS_SH_C0;
+          gs_sh_basis(deg, x, y, z, basis);
           if (deg > 0) {
-            basis[1] = -GS_SH_C1 * y;
-            basis[2] = GS_SH_C1 * z;
-            basis[3] = -GS_SH_C1 * x;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               ddx[c] = -GS_SH_C1 * sh[3 * 3 + c];
@@ -216,11 +217,6 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
               ddz[c] = GS_SH_C1 * sh[2 * 3 + c];
             }
             if (deg > 1) {
-              basis[4] = GS_C2_0 * xy;
-              basis[5] = GS_C2_1 * yz;
-              basis[6] = GS_C2_2 * (2.0f * zz - xx - yy);
-              basis[7] = GS_C2_3 * xz;
-              basis[8] = GS_C2_4 * (xx - yy);
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
                 const float sh4 = sh[4 * 3 + c], sh5 = sh[5 * 3 + c], sh6 = sh[6 * 3 + c], sh7 = sh[7 * 3 + c],
@@ -230,13 +226,6 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
                 ddz[c] += GS_C2_1 * y * sh5 + GS_C2_2 * 2.0f * 2.0f * z * sh6 + GS_C2_3 * x * sh7;
               }
               if (deg > 2) {
-                basis[9] = GS_C3_0 * y * (3.0f * xx - yy);
-                basis[10] = GS_C3_1 * xy * z;
-                basis[11] = GS_C3_2 * y * (4.0f * zz - xx - yy);
-                basis[12] = GS_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                basis[13] = GS_C3_4 * x * (4.0f * zz - xx - yy);
-                basis[14] = GS_C3_5 * z * (xx - yy);
-                basis[15] = GS_C3_6 * x * (xx - 3.0f * yy);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                   const float sh9 = sh[9 * 3 + c], sh10 = sh[10 * 3 + c], sh11 = sh[11 * 3 + c], sh12 = sh[12 * 3 + c],
@@ -256,10 +245,15 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
           }
           // all SH reads are done: the row now becomes dL_dSH (assignment, backward.py:127-213;
           // coefficients above the degree stay zero as in the zero-initialised reference buffer)
+          if (COMPACT) {
+            shc0 = make_float4(dRGB[0], dRGB[1], dRGB[2], x);
+            shc1 = make_float4(y, z, 0.0f, 0.0f);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
+            for (int k = 0; k < 16; ++k)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) sh[k * 3 + c] = basis[k] * dRGB[c];
+              for (int c = 0; c < 3; ++c) sh[k * 3 + c] = basis[k] * dRGB[c];
+          }
           sh_written = true;
           const float dd0 = gs_dot3(ddx[0], ddx[1], ddx[2], dRGB[0], dRGB[1], dRGB[2]);
           const float dd1 = gs_dot3(ddy[0], ddy[1], ddy[2], dRGB[0], dRGB[1], dRGB[2]);
@@ -322,7 +316,11 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
         o_rot = make_float4(dL_dx, dL_dy, dL_dz, dL_dr);
       }
     }
-    if (!sh_written) {
+    if (COMPACT) {
+      float4* o = reinterpret_cast<float4*>(dL_dshs) + 2 * (size_t)i;
+      o[0] = shc0;
+      o[1] = shc1;
+    } else if (!sh_written) {
 #pragma unroll
       for (int k = 0; k < 48; ++k) sh[k] = 0.0f;
     }
@@ -339,6 +337,7 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
       o[2] = make_float2(o_dcov[4], o_dcov[5]);
     }
   }
+  if (COMPACT) return;
   __syncthreads();
   {  // coalesced store of the CTA's SH gradients
     float4* dst = reinterpret_cast<float4*>(dL_dshs + (size_t)base * 48);
@@ -360,6 +359,28 @@ GSB_API int gsb_preprocess_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame*
                                     const float* dL_dmean2D, const float* dL_dconic, const float* dL_dcolor,
                                     float* dL_dmean3D, float* dL_dshs, float* dL_dscale, float* dL_drot,
                                     float* dL_dcov3D_internal) {
+  return gsb_preprocess_backward_impl(ctx, (cudaStream_t)s, f, n, means, radii, shs, scales, rotations, cov3Ds,
+                                      clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
+                                      dL_drot, dL_dcov3D_internal, 0);
+}
+
+GSB_API int gsb_preprocess_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n,
+                                               const float* means, const int32_t* radii, const float* shs,
+                                               const float* scales, const float* rotations, const float* cov3Ds,
+                                               const float* clamped_state, const float* dL_dmean2D,
+                                               const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D,
+                                               float* dL_dshs_compact, float* dL_dscale, float* dL_drot,
+                                               float* dL_dcov3D_internal) {
+  return gsb_preprocess_backward_impl(ctx, (cudaStream_t)s, f, n, means, radii, shs, scales, rotations, cov3Ds,
+                                      clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs_compact,
+                                      dL_dscale, dL_drot, dL_dcov3D_internal, 1);
+}
+
+int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
+                                 const int32_t* radii, const float* shs, const float* scales, const float* rotations,
+                                 const float* cov3Ds, const float* clamped_state, const float* dL_dmean2D,
+                                 const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D, float* dL_dshs,
+                                 float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && n >= 0, "gsb_preprocess_backward: bad frame or n");
   if (n == 0) return GSB_OK;
@@ -371,8 +392,14 @@ GSB_API int gsb_preprocess_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame*
               "gsb_preprocess_backward: dL_dcov3D_internal must be 8-byte aligned");
   FrameK k;
   gsb_make_framek(f, &k);
-  GSB_LAUNCH(ctx, preprocess_backward_kernel, (int)gsb_div_up(n, kThreads), kThreads, 0, (cudaStream_t)s, k, n, means,
-             radii, shs, scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D,
-             dL_dshs, dL_dscale, reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal);
+  if (sh_compact) {
+    GSB_LAUNCH(ctx, preprocess_backward_kernel<true>, (int)gsb_div_up(n, kThreads), kThreads, 0, s, k, n, means, radii, shs,
+               scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
+               reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal);
+  } else {
+    GSB_LAUNCH(ctx, preprocess_backward_kernel<false>, (int)gsb_div_up(n, kThreads), kThreads, 0, s, k, n, means, radii, shs,
+               scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
+               reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal);
+  }
   return GSB_OK;
 }

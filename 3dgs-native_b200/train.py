@@ -121,12 +121,16 @@ class FrameBuffers:
 
 class Trainer:
     def __init__(self, cameras, targets=None, num_points=None, params=None, config=None, device=None,
-                 rank=0, world_size=1, process_group=None, exchange="auto"):
+                 rank=0, world_size=1, process_group=None, exchange="auto", sh_compact=True):
         """``exchange`` selects how the gradient sum and the Adam step are done when world_size > 1:
         "nccl" = all_reduce + replicated Adam; "peers" / "multimem" = the fused kernel of
         gsb_adam_step_peers over symmetric memory (NVLink loads / NVSwitch in-fabric reduction);
         "auto" = peers when symmetric memory is available (measured fastest at 2 and 8 B200s:
-        4470 vs 4349 multimem vs 3986 nccl views/s at 8 GPUs), else nccl."""
+        4470 vs 4349 multimem vs 3986 nccl views/s at 8 GPUs), else nccl.
+        ``sh_compact`` (peers only): on steps where every rank renders exactly one view, the ranks
+        publish the SH gradient as its two rank-1 factors (8 instead of 48 floats per Gaussian,
+        gsb_backward_compact_sh) and the owner of a Gaussian expands them -- same bits, a third of
+        the gradient bytes over NVLink."""
         self.config = GaussianParams.get_config_dict()
         if config:
             self.config.update(config)
@@ -134,6 +138,8 @@ class Trainer:
         self.device = torch.device("cuda", self.ctx.device_index)
         self.rank, self.world_size, self.pg = rank, world_size, process_group
         self.exchange = self._pick_exchange(exchange)
+        self.sh_compact = bool(sh_compact) and self.exchange == "peers"
+        self._compact_step = False
         self.cameras = cameras
         bg = self.config["background_color"]
         self.frames = [_lib.make_frame(c["world_to_camera"], c["full_proj_matrix"], c["camera_center"], c["tan_fovx"],
@@ -198,6 +204,10 @@ class Trainer:
         self.adam_v = FlatGaussians(n, self.device)
         self.grads_tmp = None
         self.fb = None
+        self.sh_local = None
+        if self.sh_compact:       # the expanded SH gradient of this rank's shard (local scratch)
+            shard = -(-n // self.world_size) + 8
+            self.sh_local = torch.empty(48 * shard, dtype=torch.float32, device=self.device)
 
     def _frame_buffers(self, cam):
         W, H = cam["width"], cam["height"]
@@ -244,7 +254,8 @@ class Trainer:
         """backward() as called at train.py:1006-1044; parameter gradients land in ``out``."""
         frame, p = self.frames[cam_index], _lib.ptr
         P = self.params
-        rc = _lib.lib().gsb_backward(
+        fn = _lib.lib().gsb_backward_compact_sh if self._compact_step else _lib.lib().gsb_backward
+        rc = fn(
             self.ctx.h, _lib.stream_ptr(self.ctx.device_index), C.byref(frame), self.num_points, p(P["positions"]),
             p(P["opacities"]), p(P["shs"]), p(P["scales"]), p(P["rotations"]), p(fb.radii), p(fb.xy),
             p(fb.conic_opacity), p(fb.colors), p(fb.clamped_state), p(fb.cov3Ds), p(fb.point_list), p(fb.ranges),
@@ -292,11 +303,18 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def exchange_and_step(self, iteration):
-        """Gradient sum over the ranks + Adam.  nccl: all_reduce then the replicated fused Adam.
+    def exchange_and_step(self, iteration, compact=None):
+        """``compact``: the SH segment of every rank's gradient buffer holds the rank-1 factors
+        written by gsb_backward_compact_sh (None = whatever train_step decided for this step).
+
+        Gradient sum over the ranks + Adam.  nccl: all_reduce then the replicated fused Adam.
         peers / multimem: ONE kernel between two cross-rank barriers -- each rank reduces its shard
         of the gradients straight out of its peers' buffers, updates that shard, and writes the new
         parameters into every rank's buffer (gsb_adam_step_peers)."""
+        if compact is not None:
+            if compact and not (self.sh_compact and self.exchange == "peers"):
+                raise ValueError("compact SH exchange needs exchange='peers' and sh_compact=True")
+            self._compact_step = bool(compact)
         if self.exchange in ("none", "nccl"):
             self.all_reduce_gradients()
             self.optimizer_step(iteration)
@@ -317,11 +335,19 @@ class Trainer:
         G.barrier(channel=0)        # every rank's backward has finished writing its gradients
         if ev:
             ev[1].record()
-        self.ctx.check(_lib.lib().gsb_adam_step_peers(
-            self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, g_mc, p_mc,
-            _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
-            lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
-            self.config["adam_epsilon"], iteration))
+        if self._compact_step:
+            self.ctx.check(_lib.lib().gsb_adam_step_peers_compact(
+                self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, p_mc,
+                _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
+                lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
+                self.config["adam_epsilon"], iteration, _lib.ptr(self.sh_local), self.sh_local.numel(),
+                self.config["sh_degree"]))
+        else:
+            self.ctx.check(_lib.lib().gsb_adam_step_peers(
+                self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, g_mc, p_mc,
+                _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
+                lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
+                self.config["adam_epsilon"], iteration))
         if ev:
             ev[2].record()
         P.barrier(channel=1)        # every rank's parameter shard has landed everywhere
@@ -335,6 +361,8 @@ class Trainer:
         iteration of the reference loop.  Returns the device tensor holding this rank's last
         sum|render - target| (divide by 3HW for the reference's loss)."""
         mine = shard_views(list(range(len(cam_indices))), self.rank, self.world_size)
+        # one view on every rank: the SH gradient can travel as its rank-1 factors (same on all ranks)
+        self._compact_step = self.sh_compact and len(cam_indices) == self.world_size
         fb = None
         for j, b in enumerate(mine):
             ci = cam_indices[b]

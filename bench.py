@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--tile-sort", type=int, default=0, help="A/B: 0 bitonic per tile, 1 per-tile radix sort")
     ap.add_argument("--bwd-reduce", type=int, default=2, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
+    ap.add_argument("--sh-compact", type=int, default=1,
+                    help="A/B (peers exchange): 1 = SH gradients cross NVLink as their rank-1 factors, 0 = in full")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
@@ -289,7 +291,7 @@ def ours(args):
     lrs = {k: (v * lr_scale if k != "final_lr_factor" else v)
            for k, v in train.GaussianParams.lr_scheduler_config.items()}
     T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=args.exchange,
-                      config={"num_iterations": 7000, "lr_scheduler_config": lrs})
+                      sh_compact=bool(args.sh_compact), config={"num_iterations": 7000, "lr_scheduler_config": lrs})
     T.ctx.set_option("blend_cull", args.cull)
     T.ctx.set_option("bwd_reduce", args.bwd_reduce)
     T.ctx.set_option("tile_sort", args.tile_sort)
@@ -395,8 +397,8 @@ def ours(args):
                 # NCCL all-reduce + Adam) replaces adam_update -- the reference has no multi-GPU API
                 gb.backward(**scene.backward_kwargs(P.as_dict(), cam, buf, dpix, background=bg),
                             out={"dL_dmean3D": G["positions"], "dL_dscale": G["scales"], "dL_drot": G["rotations"],
-                                 "dL_dopacity": G["opacities"], "dL_dshs": G["shs"]})
-                T.exchange_and_step(it)
+                                 "dL_dopacity": G["opacities"], "dL_dshs": G["shs"]}, sh_compact=T.sh_compact)
+                T.exchange_and_step(it, compact=T.sh_compact)
             else:
                 g = gb.backward(**scene.backward_kwargs(P.as_dict(), cam, buf, dpix, background=bg))
                 lr = T.learning_rates(it)
@@ -486,7 +488,9 @@ def ours(args):
                                        "peers": " + fused NVLink peer-load gradient reduction/Adam/parameter broadcast kernel",
                                        "multimem": " + fused NVSwitch multimem gradient reduction/Adam/parameter broadcast kernel",
                                        "none": " + Adam"}[T.exchange]),
-                       "exchange": T.exchange, "exchange_plus_adam_ms": round(exchange_ms, 4), "exchange_parts": parts,
+                       "exchange": T.exchange + ("+sh_compact (SH gradients cross NVLink as their rank-1 factors: "
+                                                 "76 instead of 236 B per Gaussian and peer)" if T.sh_compact else ""),
+                       "exchange_plus_adam_ms": round(exchange_ms, 4), "exchange_parts": parts,
                        "views_per_step": world, "num_rendered_view0": int(num_rendered), "densify": "off (fixed N)",
                        "learning_rates": "reference values x 1e-4 (keeps the synthetic scene at the named shape)",
                        "l2": "per-step working set ~0.5 GB (params, grads, Adam state, binning buffers) > 126 MB L2; "

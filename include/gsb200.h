@@ -180,6 +180,29 @@ int gsb_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, cons
                  float* dL_dcolor, float* dL_dshs, float* dL_dopacity, float* dL_dscale, float* dL_drot,
                  float* dL_dmean2D, float* dL_dconic, float* dL_dcov3D, const int32_t* block_masks /* optional */);
 
+/* gsb_preprocess_backward with the SH gradient in COMPACT form (see gsb_backward_compact_sh):
+ * dL_dshs_compact is float[N][8]. */
+int gsb_preprocess_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const float* means,
+                                       const int32_t* radii, const float* shs, const float* scales,
+                                       const float* rotations, const float* cov3Ds, const float* clamped_state,
+                                       const float* dL_dmean2D, const float* dL_dconic, const float* dL_dcolor,
+                                       float* dL_dmean3D, float* dL_dshs_compact, float* dL_dscale, float* dL_drot,
+                                       float* dL_dcov3D_internal);
+
+/* gsb_backward with the SH gradient in COMPACT form (no reference counterpart; used by the view-sharded
+ * trainer).  For one view the reference's dL_dshs[16 i + k] = basis_k(dir_i) * dL_dRGB_i
+ * (sh_backward_kernel, backward.py:116-213) is a rank-1 product, so dL_dshs here receives only its two
+ * factors: float[N][8] = (dL_dRGB after the clamp mask, unit view direction, 0, 0); zeros for a
+ * Gaussian the reference skips.  Everything else is identical to gsb_backward. */
+int gsb_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const float* means,
+                            const float* opacities, const float* shs, const float* scales, const float* rotations,
+                            const int32_t* radii, const float* points_xy, const float* conic_opacity, const float* rgb,
+                            const float* clamped_state, const float* cov3Ds, const int32_t* point_list,
+                            const int32_t* ranges, const float* final_T, const int32_t* n_contrib,
+                            const float* dL_dpixels, float* dL_dmean3D, float* dL_dcolor, float* dL_dshs,
+                            float* dL_dopacity, float* dL_dscale, float* dL_drot, float* dL_dmean2D, float* dL_dconic,
+                            float* dL_dcov3D, const int32_t* block_masks /* optional */);
+
 /* ---- optimizer / densify (optimizer.py, train.py nested kernels) -------------------------- */
 
 /* replaces adam_update (optimizer.py:6-139, launched train.py:750-794); in place. */
@@ -208,6 +231,19 @@ int gsb_adam_step_peers(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, in
                         uint64_t param_multicast, float* m_flat, float* v_flat, float lr_pos, float lr_scale,
                         float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
                         int32_t iteration);
+
+/* gsb_adam_step_peers for gradient buffers written by gsb_backward_compact_sh: the SH segment of every
+ * rank's flat gradient buffer starts with that rank's float[N][8] factors.  The owner of a Gaussian
+ * rebuilds each rank's 48 SH gradients from them (same basis code as the backward, same rank order of
+ * the sum as gsb_adam_step_peers: identical bits) into sh_local -- device scratch of sh_local_floats >=
+ * 48 * (Gaussians of this rank's shard) floats, need not be peer-visible -- and the fused exchange + Adam
+ * reads its SH gradient from there.  NVLink carries 76 instead of 236 bytes per Gaussian and peer on the
+ * gradient side.  Valid when every rank contributed exactly ONE view (the factors of two views do not add). */
+int gsb_adam_step_peers_compact(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, int32_t rank,
+                                const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host,
+                                uint64_t param_multicast, float* m_flat, float* v_flat, float lr_pos, float lr_scale,
+                                float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
+                                int32_t iteration, float* sh_local, int64_t sh_local_floats, int32_t degree);
 
 /* replaces zero_gradients (train.py:94-115) -- and any other "fill float" need */
 int gsb_fill_f32(gsb_ctx* ctx, gsb_stream s, float* dst, int64_t count, float value);

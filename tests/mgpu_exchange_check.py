@@ -25,15 +25,15 @@ def main():
     rng = np.random.default_rng(7)
     targets = [rng.uniform(0, 1, (h, w, 3)).astype(np.float32) for _ in cams]
     results = {}
-    modes = ["nccl", "peers"]
+    modes = ["nccl", "peers", "peers_full"]    # "peers" = default (compact SH exchange), "peers_full" = sh_compact off
     probe = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange="auto")
     assert probe.exchange == "peers"
     if int(getattr(probe.params.symm, "multicast_ptr", 0) or 0) != 0:
         modes.append("multimem")
     for mode in modes:
-        T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=mode,
-                          config={"num_iterations": 100})
-        assert T.exchange == mode
+        T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world,
+                          exchange=mode.split("_")[0], sh_compact=(mode == "peers"), config={"num_iterations": 100})
+        assert T.exchange == mode.split("_")[0] and T.sh_compact == (mode == "peers")
         for it in range(steps):
             T.train_step(it, [(it * world + r) % len(cams) for r in range(world)], densify=False)
         torch.cuda.synchronize()
@@ -43,6 +43,8 @@ def main():
         dist.all_gather(gathered, results[mode])
         for g in gathered:
             assert torch.equal(g, gathered[0]), f"{mode}: replicas differ between ranks"
+    # the compact SH exchange rebuilds the same products and adds them in the same rank order: same bits
+    assert torch.equal(results["peers"], results["peers_full"]), "compact SH exchange differs from the full one"
     ref = results["nccl"].double()
     for mode in modes[1:]:
         d = (results[mode].double() - ref).norm() / ref.norm()

@@ -252,3 +252,66 @@ def test_ssim_and_depth_loss_vs_golden_and_oracle(gs, golden_dir, oracle):
         want = oracle.depth_loss(rd, td, m)
         got = gs.loss.depth_loss(rd, td, m)
         assert abs(got - want) <= 1e-7 * h * w + 5e-6, (h, w, got, want)
+
+
+@pytest.mark.parametrize("degree", [3, 1])
+def test_compact_sh_gradient_expands_to_the_same_bits(gs, degree):
+    """gsb_backward_compact_sh publishes the SH gradient as its two rank-1 factors (8 floats per Gaussian);
+    gsb_adam_step_peers_compact rebuilds the 48 products on the owner's side.  With a world of one rank
+    (no peer mapping needed) parameters and Adam moments must come out bit-identical to the full
+    exchange kernel fed with the full gradient -- incl. culled Gaussians (all-zero factors), a degree
+    below 3 and a Gaussian count that is not a multiple of 4."""
+    import ctypes as C
+    from gsb200 import _lib, backward, forward
+    n, w, h = 6001, 128, 96
+    params, cam, target = gs.scene.synthetic_scene(n, w, h, 0.01, 0.08, seed=11)
+    kw = gs.scene.render_kwargs(params, cam)
+    kw["degree"] = degree
+    img, _d, buf = forward.render_gaussians(**kw)
+    dpix = torch.from_numpy(np.random.default_rng(3).normal(size=(h, w, 3)).astype(np.float32)).cuda()
+    FG = gs.train.FlatGaussians
+    dev = img.device
+    bkw = gs.scene.backward_kwargs(params, cam, buf, dpix)
+    bkw["degree"] = degree
+    # the tile stage once (its atomics make two runs differ in the last bits); both forms of the
+    # per-Gaussian stage then start from the same dL_dmean2D / dL_dconic / dL_dcolor
+    g = backward.backward(**bkw)
+    ctx = _lib.context()
+    stream, p = _lib.stream_ptr(ctx.device_index), _lib.ptr
+    frame = _lib.make_frame(cam["world_to_camera"], cam["full_proj_matrix"], cam["camera_center"], cam["tan_fovx"],
+                            cam["tan_fovy"], w, h, (0.0, 0.0, 0.0), degree, True, 1.0)
+    dparams = {k: _lib.to_device(params[k], device=dev) for k in KEYS}
+    runs = {}
+    for compact in (False, True):
+        G, P, M, V = FG(n, dev), FG(n, dev).load(params), FG(n, dev), FG(n, dev)
+        G.flat.fill_(123.0)        # the compact form must not depend on what the buffer held before
+        M.flat.uniform_(-1e-3, 1e-3, generator=torch.Generator(device=dev).manual_seed(1))
+        V.flat.uniform_(0, 1e-5, generator=torch.Generator(device=dev).manual_seed(2))
+        fn = _lib.lib().gsb_preprocess_backward_compact_sh if compact else _lib.lib().gsb_preprocess_backward
+        ctx.check(fn(ctx.h, stream, C.byref(frame), n, p(dparams["positions"]), p(buf["radii"]), p(dparams["shs"]),
+                     p(dparams["scales"]), p(dparams["rotations"]), p(buf["cov3Ds"]), p(buf["clamped_state"]),
+                     p(g["dL_dmean2D"]), p(g["dL_dconic"]), p(g["dL_dcolor"]), p(G["positions"]), p(G["shs"]),
+                     p(G["scales"]), p(G["rotations"]), p(None)))
+        G["opacities"].copy_(g["dL_dopacity"].view_as(G["opacities"]))
+        gp, pp = (C.c_uint64 * 1)(G.flat.data_ptr()), (C.c_uint64 * 1)(P.flat.data_ptr())
+        lrs = (1e-2, 5e-3, 5e-3, 5e-3, 2e-3)
+        if compact:
+            scratch = torch.empty(48 * (n + 8), dtype=torch.float32, device=dev)
+            ctx.check(_lib.lib().gsb_adam_step_peers_compact(
+                ctx.h, stream, n, 1, 0, gp, pp, 0, p(M.flat), p(V.flat), *lrs, 0.9, 0.999, 1e-8, 5, p(scratch),
+                scratch.numel(), degree))
+        else:
+            ctx.check(_lib.lib().gsb_adam_step_peers(
+                ctx.h, stream, n, 1, 0, gp, pp, 0, 0, p(M.flat), p(V.flat), *lrs, 0.9, 0.999, 1e-8, 5))
+        torch.cuda.synchronize()
+        runs[compact] = (P.flat.clone(), M.flat.clone(), V.flat.clone(), G)
+    assert torch.equal(runs[False][3]["shs"].reshape(-1), g["dL_dshs"].reshape(-1))   # the stage call = the operator
+    for a, b, name in zip(runs[False][:3], runs[True][:3], ("params", "m", "v")):
+        assert torch.equal(a, b), name
+    # and the factors themselves: dRGB x basis_0 (= SH_C0, exact constant) is the DC row of the full gradient
+    full_sh = runs[False][3]["shs"].view(n, 16, 3)
+    fac = runs[True][3]["shs"].reshape(-1)[:8 * n].view(n, 8)
+    assert torch.equal(full_sh[:, 0, :], fac[:, :3] * np.float32(0.28209479177387814))
+    norm = fac[:, 3:6].norm(dim=1)
+    live = norm > 0
+    assert bool(((norm[live] - 1).abs() < 1e-5).all()) and bool((fac[:, 6:] == 0).all())

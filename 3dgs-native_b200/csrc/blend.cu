@@ -26,7 +26,12 @@
 // warp reduces the nine live gradient scalars with a transposed butterfly (9 + 5 shuffles instead of
 // 45), and nine lanes issue one RED each per (warp, Gaussian) -- and only for Gaussians that
 // touched the warp at all.
+#include <type_traits>
+
 #include "blend_common.cuh"
+#include "tilesort.cuh"
+
+extern int g_fuse_sort;
 
 namespace {
 
@@ -43,8 +48,21 @@ struct FwdSmem {
   unsigned char widx[8][256];  // per warp: the staged entries that touch its block
 };
 
+constexpr int kFusedSortMax = 2048;  // longest tile list the fused prologue sorts: 8 B x 2048 = the blend's own 16 KB
+
+// SORT: the CTA first sorts its own tile's segment of the binned list (tile_sort_segment, the body of
+// tile_sort_kernel) in the shared memory it later stages Gaussians in, writes the tile's part of point_list
+// -- an output of the operator -- and goes on to blend from it.  The sort is a chain of shared-memory
+// round trips and barriers that leaves most issue slots idle (48 us as a kernel of its own); the idea was
+// that inside this kernel those slots are filled by the other resident CTAs, which are blending.
+// MEASURED (B200, headline scene): forward 368 us against 359 us with the separate tile_sort_kernel -- the
+// bitonic network adds 12% to the instructions of a kernel that is issue-bound already.  A/B option
+// (gsb_set_option("fuse_sort", 1)), not the default.
+template <bool SORT>
 __global__ void __launch_bounds__(256, GSB_FWD_MINB)
-blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
+blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges,
+                     typename std::conditional<SORT, int*, const int* __restrict__>::type point_list,
+                     const unsigned long long* __restrict__ binned,
                      const float2* __restrict__ xy, const float* __restrict__ rgb,
                      const float4* __restrict__ conic_opacity, const float* __restrict__ depths,
                      float* __restrict__ image, float* __restrict__ inv_depth, float* __restrict__ final_T,
@@ -73,6 +91,10 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
 
   const int2 range = ranges[tile_id];
   const int todo = range.y - range.x;
+  if (SORT && todo > 0) {
+    tile_sort_segment(range, binned, const_cast<int*>(point_list), reinterpret_cast<unsigned long long*>(smem_raw));
+    __syncthreads();  // point_list is read back below (plain loads: this CTA wrote it), smem_raw is reused
+  }
   const unsigned char* const wlist = sm.widx[warp];
   for (int base = 0; base < todo; base += NT) {
     if (__syncthreads_and(done)) break;
@@ -200,6 +222,26 @@ GSB_API int gsb_selftest_block_mask(gsb_ctx* ctx, gsb_stream s, int32_t count, c
   return GSB_OK;
 }
 
+// gsb_blend_forward whose CTAs sort their tile's segment of `binned` (the scattered, unsorted
+// (depth_bits << 32 | id) list) into point_list first.  Precondition: no tile list longer than
+// gsb_blend_forward_fused_sort_max().
+int gsb_blend_forward_sorting(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, const int32_t* ranges,
+                              const unsigned long long* binned, int32_t* point_list, const float* points_xy,
+                              const float* rgb, const float* conic_opacity, const float* depths, float* image,
+                              float* inv_depth, float* final_T, int32_t* n_contrib, int32_t* block_masks) {
+  GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0, "gsb_blend_forward: bad frame");
+  GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_forward: conic_opacity must be 16-byte aligned");
+  static_assert(sizeof(FwdSmem) >= kFusedSortMax * sizeof(unsigned long long), "the sort buffer aliases the staging arrays");
+  BlendParams P = make_blend_params(f);
+  dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
+  GSB_LAUNCH(ctx, blend_forward_kernel<true>, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
+             point_list, binned, reinterpret_cast<const float2*>(points_xy), rgb,
+             reinterpret_cast<const float4*>(conic_opacity), depths, image, inv_depth, final_T, n_contrib,
+             reinterpret_cast<unsigned*>(block_masks));
+  return GSB_OK;
+}
+int gsb_blend_forward_fused_sort_max() { return g_fuse_sort ? kFusedSortMax : 0; }
+
 GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* rgb,
                               const float* conic_opacity, const float* depths, float* image, float* inv_depth,
@@ -210,8 +252,8 @@ GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, c
   cudaStream_t s = (cudaStream_t)s_;
   BlendParams P = make_blend_params(f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  GSB_LAUNCH(ctx, blend_forward_kernel, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges), point_list,
-             reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity), depths,
+  GSB_LAUNCH(ctx, blend_forward_kernel<false>, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
+             point_list, nullptr, reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity), depths,
              image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks));
   return GSB_OK;
 }

@@ -18,7 +18,7 @@
 // Traffic: 8 B written + 8 B read + 4 B written per duplicate, instead of 32 B per duplicate per
 // radix pass (6 passes at 800x800).  Tiles longer than kMaxTileSort fall back to the global radix
 // sort (sort.cu), which is also what the stage-level entry point gsb_sort_pairs64 runs.
-#include "common.cuh"
+#include "tilesort.cuh"
 
 extern int g_tile_sort;
 constexpr int kMaxTileSort = 16384;
@@ -123,17 +123,7 @@ tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restric
     }
 }
 
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
-  unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
-  unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
-  return ((unsigned long long)hi << 32) | lo;
-}
-
-// One CTA per tile: bitonic sort of the segment's (depth_bits<<32 | id) composites.
-// A warp owns whole 64-element chunks (dealt round-robin); in chunk c lane l holds elements
-// e0 = 64c + l and e1 = e0 + 32.  Compare-exchange strides j < 32 are shuffles, j == 32 is
-// in-thread, j >= 64 goes through shared memory.  Direction of element i in merge size k:
-// ascending iff (i & k) == 0 (automatically true for the final merge k == n_pad).
+// One CTA per tile: see tile_sort_segment (tilesort.cuh).
 template <int CAP>
 __global__ void __launch_bounds__(256)
 tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
@@ -142,76 +132,7 @@ tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __re
   const int2 rg = ranges[blockIdx.x];
   const int count = rg.y - rg.x;
   if (count <= lo || count > hi) return;  // empty, or a tile another launch sorts
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (count == 1) {
-    if (tid == 0) point_list[rg.x] = (int)(unsigned)binned[rg.x];
-    return;
-  }
-  int n_pad = 64;
-  while (n_pad < count) n_pad <<= 1;  // <= CAP by construction (host checked the max count)
-  const int chunks = n_pad >> 6;
-
-  // ---- phase 1: sort every 64-element chunk in registers (k = 2 .. 64)
-  for (int c = warp; c < chunks; c += 8) {
-    const int e0 = (c << 6) + lane, e1 = e0 + 32;
-    unsigned long long a = (e0 < count) ? binned[rg.x + e0] : ~0ull;
-    unsigned long long b = (e1 < count) ? binned[rg.x + e1] : ~0ull;
-#pragma unroll
-    for (int k = 2; k <= 64; k <<= 1) {
-      const bool asc0 = (e0 & k) == 0, asc1 = (e1 & k) == 0;
-      if (k == 64 && ((a > b) == asc0)) {  // stride 32: the partner is this thread's other element
-        const unsigned long long t = a;
-        a = b;
-        b = t;
-      }
-#pragma unroll
-      for (int j = (k == 64 ? 16 : k >> 1); j > 0; j >>= 1) {
-        const unsigned long long pa = shfl_xor_u64(a, j), pb = shfl_xor_u64(b, j);
-        const bool lower = (lane & j) == 0;
-        a = ((a < pa) == (lower == asc0)) ? a : pa;  // lower half keeps the min when ascending
-        b = ((b < pb) == (lower == asc1)) ? b : pb;
-      }
-    }
-    s_key[e0] = a;
-    s_key[e1] = b;
-  }
-  // ---- phase 2: merges k = 128 .. n_pad; strides >= 64 through shared memory, the rest in registers
-  for (int k = 128; k <= n_pad; k <<= 1) {
-    for (int j = k >> 1; j >= 64; j >>= 1) {
-      __syncthreads();
-      for (int i = tid; i < (n_pad >> 1); i += 256) {
-        const int l = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-        const int r = l + j;
-        const unsigned long long a = s_key[l], b = s_key[r];
-        if ((a > b) == ((l & k) == 0)) {
-          s_key[l] = b;
-          s_key[r] = a;
-        }
-      }
-    }
-    __syncthreads();
-    for (int c = warp; c < chunks; c += 8) {
-      const int e0 = (c << 6) + lane, e1 = e0 + 32;
-      unsigned long long a = s_key[e0], b = s_key[e1];
-      const bool asc = (e0 & k) == 0;
-      if ((a > b) == asc) {
-        const unsigned long long t = a;
-        a = b;
-        b = t;
-      }
-#pragma unroll
-      for (int j = 16; j > 0; j >>= 1) {
-        const unsigned long long pa = shfl_xor_u64(a, j), pb = shfl_xor_u64(b, j);
-        const bool lower = (lane & j) == 0;
-        a = ((a < pa) == (lower == asc)) ? a : pa;
-        b = ((b < pb) == (lower == asc)) ? b : pb;
-      }
-      s_key[e0] = a;
-      s_key[e1] = b;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < count; i += 256) point_list[rg.x + i] = (int)(unsigned)s_key[i];
+  tile_sort_segment(rg, binned, point_list, s_key);
 }
 
 // One CTA per tile: stable LSD radix sort of the segment by the 32 depth bits (8 bits per pass, passes
@@ -424,6 +345,8 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                           const float* depths, const int32_t* radii, const int32_t* rank_index,
                           int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
                           int32_t* point_list) {
+  // point_list == nullptr: scatter only -- the caller's forward tile kernel sorts each tile itself
+  // (gsb_blend_forward_sorting) from gsb_tile_binning_binned()
   const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
   const int num_tiles = gx * gy;
   // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
@@ -432,6 +355,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   GSB_LAUNCH(ctx, tile_scatter_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
              depths, radii, rank_index, index_is_exclusive, gx, gy, rg, ctx->vals_a, binned);
   (void)num_rendered;
+  if (!point_list) return GSB_OK;
   // Per-tile sort.  Default: the bitonic kernel.  g_tile_sort == 1 (A/B switch): the O(n) shared-memory
   // radix sort for tiles of up to 4096 entries and the bitonic kernel for longer ones (each kernel
   // skips the other's tiles).  Measured on a B200 at ~650 entries per tile the radix kernel executes
@@ -478,3 +402,4 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
 }
 
 int gsb_tile_binning_max() { return kMaxTileSort; }
+const unsigned long long* gsb_tile_binning_binned(gsb_ctx* ctx) { return reinterpret_cast<const unsigned long long*>(ctx->keys_a); }

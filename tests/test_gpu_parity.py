@@ -160,6 +160,28 @@ def test_backward_reduction_modes_agree_with_oracle(gs, oracle, mode, hand_masks
         _lib.context().set_option("bwd_reduce", 2)
 
 
+@pytest.mark.parametrize("n,w,h,smin,smax", [(20000, 320, 240, 0.005, 0.05), (3000, 100, 70, 0.05, 0.4)])
+def test_fused_and_separate_tile_sort_give_the_same_bits(gs, n, w, h, smin, smax):
+    """fuse_sort = 1 (A/B option, measured slower): the forward tile kernel's CTAs sort their own tile's list
+    (lists of up to 2048 entries; the second scene has longer ones and falls back by itself); 0 (default):
+    tile_sort_kernel does.  Every output of the operator must be bit-identical between the two."""
+    from gsb200 import _lib
+    params, cam, _ = gs.scene.synthetic_scene(n, w, h, smin, smax, seed=n + 3 * w)
+    kw = gs.scene.render_kwargs(params, cam)
+    outs = []
+    try:
+        for fuse in (1, 0):
+            _lib.context().set_option("fuse_sort", fuse)
+            img, dep, buf = gs.forward.render_gaussians(**kw)
+            outs.append((img, dep, buf))
+    finally:
+        _lib.context().set_option("fuse_sort", 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][2]["point_list"].numel() > 0
+    for k in outs[0][2]:
+        assert torch.equal(outs[0][2][k], outs[1][2][k]), k
+
+
 def test_backward_writes_into_caller_buffers(gs):
     """backward(out=...) (our extension): results land in the given tensors, the others are allocated."""
     params, cam, target = gs.scene.synthetic_scene(3000, 96, 64, 0.01, 0.1, seed=3)

@@ -31,6 +31,7 @@ int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default);
 int g_blend_cull = 1;
 int g_tile_sort = 0;   // 0: bitonic network for every tile (default); 1: per-tile LSD radix sort (bitonic for tiles > 4096)
 int g_bwd_reduce = 2;
+int g_bwd_packed = 1;  // 1: tensor-core backward accumulates into packed records with vector REDs (default); 0: nine scalar REDs
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -84,13 +85,15 @@ int gsb_reserve_binning(gsb_ctx* ctx, cudaStream_t s, int64_t num_rendered) {
 
 static int reserve_per_gaussian(gsb_ctx* ctx, cudaStream_t s, int64_t n) {
   if (n <= ctx->n_cap) return GSB_OK;
-  int64_t c0 = ctx->n_cap, c1 = ctx->n_cap, c2 = ctx->n_cap;
+  int64_t c0 = ctx->n_cap, c1 = ctx->n_cap, c2 = ctx->n_cap, c3 = ctx->n_cap * 12;
   int rc;
+  if ((rc = gsb_grow(ctx, (void**)&ctx->bwd_acc, &c3, n * 12, sizeof(float), s)) != GSB_OK) return rc;
   if ((rc = gsb_grow(ctx, (void**)&ctx->tiles_touched, &c0, n, sizeof(int32_t), s)) != GSB_OK) return rc;
   if ((rc = gsb_grow(ctx, (void**)&ctx->dcov3d, &c1, n * 6, sizeof(float), s)) != GSB_OK) return rc;
   if ((rc = gsb_grow(ctx, (void**)&ctx->rank_base, &c2, n, sizeof(int32_t), s)) != GSB_OK) return rc;
   ctx->n_cap = c0 < c1 / 6 ? c0 : c1 / 6;
   ctx->n_cap = ctx->n_cap < c2 ? ctx->n_cap : c2;
+  ctx->n_cap = ctx->n_cap < c3 / 12 ? ctx->n_cap : c3 / 12;
   return GSB_OK;
 }
 
@@ -139,6 +142,8 @@ GSB_API int gsb_destroy(gsb_ctx* ctx) {
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->rank_base) cudaFree(ctx->rank_base);
+  if (ctx->bwd_acc) cudaFree(ctx->bwd_acc);
+  if (ctx->bwd_acc_stage) cudaFree(ctx->bwd_acc_stage);
   if (ctx->ev_count) cudaEventDestroy(ctx->ev_count);
   delete ctx;
   return GSB_OK;
@@ -165,6 +170,10 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
   }
   if (!strcmp(name, "tile_sort") && (value == 0 || value == 1)) {
     g_tile_sort = value;
+    return GSB_OK;
+  }
+  if (!strcmp(name, "bwd_packed") && (value == 0 || value == 1)) {
+    g_bwd_packed = value;
     return GSB_OK;
   }
   if (!strcmp(name, "fuse_sort") && (value == 0 || value == 1)) {
@@ -335,14 +344,20 @@ static int backward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_
   if (n == 0) return GSB_OK;
   int rc;
   if ((rc = reserve_per_gaussian(ctx, s, n)) != GSB_OK) return rc;
-  // backward.py:1135-1152
-  rc = gsb_blend_backward(ctx, s_, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
-                          dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, block_masks);
+  // backward.py:1135-1152.  Default: the tile kernel accumulates into packed per-Gaussian records (vector REDs)
+  // and the per-Gaussian pass writes dL_dmean2D / dL_dconic / dL_dcolor / dL_dopacity out in the reference's layouts.
+  const bool packed = gsb_blend_backward_uses_packed();
+  if (packed)
+    rc = gsb_blend_backward_packed(ctx, s, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
+                                   dL_dpixels, ctx->bwd_acc, block_masks);
+  else
+    rc = gsb_blend_backward(ctx, s_, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
+                            dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, block_masks);
   if (rc != GSB_OK) return rc;
   // backward.py:1155-1182
   rc = gsb_preprocess_backward_impl(ctx, s, f, n, means, radii, shs, scales, rotations, cov3Ds, clamped_state,
                                     dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, dL_drot, nullptr,
-                                    sh_compact);
+                                    sh_compact, packed ? ctx->bwd_acc : nullptr, dL_dopacity);
   if (rc != GSB_OK) return rc;
   // backward.py:1119,1195: the returned dL_dcov3D is a fresh zero buffer no kernel writes
   if (dL_dcov3D) GSB_CUDA(ctx, cudaMemsetAsync(dL_dcov3D, 0, sizeof(float) * 6 * (size_t)n, s));

@@ -257,7 +257,19 @@ __device__ __forceinline__ void mma_tf32_k4(float d[4], float a0, float a1, floa
 
 __device__ __forceinline__ float f4_get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
 
-template <int MINB>  // resident CTAs per SM the register budget is cut for: 3 (80 registers) or 4 (64)
+// 16-byte vector reduction (sm_90+): four float adds at one 16-byte-aligned address in ONE instruction and one
+// L2 sector operation (REDG.E.ADD.F32x4, same FTZ.RN flavour as the scalar RED atomicAdd compiles to).
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// PACKED: the nine sums of a flushed Gaussian go to ONE 48-byte record
+//   acc[12 gid + 0..3] = dL_dconic a, b, c, dL_dopacity      acc[+4..7] = dL_dcolor r, g, b, dL_dmean2D x
+//   acc[+8] = dL_dmean2D y                                    (+9..11 unused)
+// with two vector REDs and one scalar RED instead of nine scalar REDs into four arrays: per flush the 16 lanes
+// touch 48 instead of 144 sectors (the replay is co-limited by the LSU data pipe, profiles/r01_ncu_bwd_warp_
+// autonomous.md).  preprocess_backward_kernel<.., PACKED> unpacks the record into the reference's arrays.
+template <int MINB, bool PACKED>  // MINB: resident CTAs per SM the register budget is cut for: 3 (80 registers) or 4 (64)
 __global__ void __launch_bounds__(256, MINB)
 blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -265,7 +277,7 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
                           const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
                           float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
-                          const unsigned* __restrict__ block_masks) {
+                          const unsigned* __restrict__ block_masks, float* __restrict__ acc_packed) {
   constexpr int NT = 256, NW = 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -440,15 +452,25 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
         const float Sdxy = ux * Sdy - uy * Si + Sir;
         const float Sdyy = uy * (Sdy - Sr) + Srr;
         const float o = gb.y;  // dL_dG = opacity * dL_dalpha (backward.py:683)
-        atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
-        atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
-        atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
-        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx);   // backward.py:691-695
-        atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy);
-        atomicAdd(dL_dconic + 4 * (size_t)gid + 0, -0.5f * o * Sdxx);                              // backward.py:698-703
-        atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * o * Sdxy);
-        atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * o * Sdyy);
-        atomicAdd(dL_dopacity + gid, S0);                                                           // backward.py:706
+        const float gmx = -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx;   // backward.py:691-695
+        const float gmy = -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy;
+        const float gca = -0.5f * o * Sdxx, gcb = -0.5f * o * Sdxy, gcc = -0.5f * o * Sdyy;   // backward.py:698-703
+        if (PACKED) {
+          float* const rec = acc_packed + 12 * (size_t)gid;
+          red_add_v4(rec, gca, gcb, gcc, S0);
+          red_add_v4(rec + 4, col.x, col.y, col.z, gmx);
+          atomicAdd(rec + 8, gmy);
+        } else {
+          atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
+          atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
+          atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
+          atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, gmx);
+          atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, gmy);
+          atomicAdd(dL_dconic + 4 * (size_t)gid + 0, gca);
+          atomicAdd(dL_dconic + 4 * (size_t)gid + 1, gcb);
+          atomicAdd(dL_dconic + 4 * (size_t)gid + 3, gcc);
+          atomicAdd(dL_dopacity + gid, S0);   // backward.py:706
+        }
       }
       __syncwarp();  // results consumed before the next group overwrites the tile
       gslot = 0;
@@ -778,6 +800,25 @@ blend_backward_warp_kernel(const BlendParams P, const int2* __restrict__ ranges,
   if (gslot > 0) flush_group(rd - gslot, gslot);
 }
 
+// Stage-level entry point only: the packed records written out in the reference's four layouts (inside
+// gsb_backward the per-Gaussian pass does this on the fly).
+__global__ void __launch_bounds__(256)
+unpack_records_kernel(int n, const float4* __restrict__ acc, float* __restrict__ dL_dmean2D, float4* __restrict__ dL_dconic,
+                      float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q0 = acc[3 * (size_t)i], q1 = acc[3 * (size_t)i + 1];
+  const float my = reinterpret_cast<const float*>(acc + 3 * (size_t)i + 2)[0];
+  dL_dconic[i] = make_float4(q0.x, q0.y, 0.0f, q0.z);
+  dL_dopacity[i] = q0.w;
+  dL_dcolor[3 * (size_t)i + 0] = q1.x;
+  dL_dcolor[3 * (size_t)i + 1] = q1.y;
+  dL_dcolor[3 * (size_t)i + 2] = q1.z;
+  dL_dmean2D[3 * (size_t)i + 0] = q1.w;
+  dL_dmean2D[3 * (size_t)i + 1] = my;
+  dL_dmean2D[3 * (size_t)i + 2] = 0.0f;
+}
+
 // The four accumulation targets of the tile kernel zeroed by ONE launch (four memsets were four stream
 // operations of ~2 us each in front of a 0.3 ms kernel).  16-byte stores over each array's aligned body.
 struct ZeroJob {
@@ -803,6 +844,59 @@ __global__ void __launch_bounds__(256) zero_arrays_kernel(const ZeroJob job) {
 
 }  // namespace
 
+extern int g_bwd_packed;
+bool gsb_blend_backward_uses_packed() { return g_bwd_packed != 0 && (g_bwd_reduce == 1 || g_bwd_reduce == 2); }
+
+// The tensor-core kernel, either accumulating into the caller's four arrays (packed == nullptr; they must be
+// zero) or into packed records (which must be zero).
+static int launch_backward_mma(gsb_ctx* ctx, cudaStream_t s, const BlendParams& P, dim3 grid, const int32_t* ranges,
+                               const int32_t* point_list, const float* points_xy, const float* conic_opacity,
+                               const float* rgb, const float* final_T, const int32_t* n_contrib,
+                               const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                               float* dL_dcolor, const unsigned* masks, float* packed) {
+  bool& attr_set = ctx->smem_optin_blend_bwd;  // > 48 KB of dynamic shared memory needs the opt-in (per device)
+  if (!attr_set) {
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    attr_set = true;
+  }
+#define GSB_BWD_MMA(MINB, PK)                                                                                              \
+  GSB_LAUNCH(ctx, (blend_backward_mma_kernel<MINB, PK>), grid, 256, sizeof(BwdSmem), s, P,                                  \
+             reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),               \
+             reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic,  \
+             dL_dopacity, dL_dcolor, masks, packed)
+  if (g_bwd_reduce == 2) {
+    if (packed) GSB_BWD_MMA(4, true);
+    else GSB_BWD_MMA(4, false);
+  } else {
+    if (packed) GSB_BWD_MMA(3, true);
+    else GSB_BWD_MMA(3, false);
+  }
+#undef GSB_BWD_MMA
+  return GSB_OK;
+}
+
+int gsb_blend_backward_packed(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const int32_t* ranges,
+                              const int32_t* point_list, const float* points_xy, const float* conic_opacity,
+                              const float* rgb, const float* final_T, const int32_t* n_contrib,
+                              const float* dL_dpixels, float* packed, const int32_t* block_masks) {
+  GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0 && n >= 0, "gsb_blend_backward: bad frame");
+  GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity) && gsb_aligned16(packed), "gsb_blend_backward: 16-byte alignment");
+  if (n == 0) return GSB_OK;
+  ZeroJob job;
+  for (int a = 0; a < 4; ++a) job.p[a] = packed, job.n[a] = 0;
+  job.n[0] = 12LL * n;
+  const long long blocks = gsb_div_up(3LL * n, 256);  // one 16-byte store per thread
+  GSB_LAUNCH(ctx, zero_arrays_kernel, (unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, s, job);
+  BlendParams P = make_blend_params(f);
+  dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
+  return launch_backward_mma(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
+                             dL_dpixels, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const unsigned*>(block_masks),
+                             packed);
+}
+
 GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const int32_t* ranges,
                                const int32_t* point_list, const float* points_xy, const float* conic_opacity,
                                const float* rgb, const float* final_T, const int32_t* n_contrib,
@@ -813,6 +907,20 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_backward: conic_opacity must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)s_;
   if (n == 0) return GSB_OK;
+  if (gsb_blend_backward_uses_packed() && gsb_aligned16(dL_dconic)) {
+    // stage-level call of the default path: packed records in context scratch, then written out
+    if (ctx->bwd_acc_cap < 12LL * n) {
+      int rc = gsb_grow(ctx, (void**)&ctx->bwd_acc_stage, &ctx->bwd_acc_cap, 12LL * n, sizeof(float), s);
+      if (rc != GSB_OK) return rc;
+    }
+    int rc = gsb_blend_backward_packed(ctx, s, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
+                                       dL_dpixels, ctx->bwd_acc_stage, block_masks);
+    if (rc != GSB_OK) return rc;
+    GSB_LAUNCH(ctx, unpack_records_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n,
+               reinterpret_cast<const float4*>(ctx->bwd_acc_stage), dL_dmean2D, reinterpret_cast<float4*>(dL_dconic),
+               dL_dopacity, dL_dcolor);
+    return GSB_OK;
+  }
   {
     ZeroJob job;
     job.p[0] = dL_dmean2D, job.n[0] = 3LL * n;
@@ -831,7 +939,6 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
                n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, masks);
     return GSB_OK;
   }
-  bool& attr_set = ctx->smem_optin_blend_bwd;  // > 48 KB of dynamic shared memory needs the opt-in (per device)
   if (g_bwd_reduce >= 3) {  // warp-autonomous replay: 3 = four warps per CTA (seven CTAs per SM), 4 = eight (three)
     const long long tiles = (long long)grid.x * grid.y;
     if (g_bwd_reduce == 3) {
@@ -852,23 +959,6 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
     }
     return GSB_OK;
   }
-  if (!attr_set) {
-    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BwdSmem)));
-    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BwdSmem)));
-    attr_set = true;
-  }
-  if (g_bwd_reduce == 2) {
-    GSB_LAUNCH(ctx, blend_backward_mma_kernel<4>, grid, 256, sizeof(BwdSmem), s, P,
-               reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
-               reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
-               dL_dconic, dL_dopacity, dL_dcolor, masks);
-  } else {
-    GSB_LAUNCH(ctx, blend_backward_mma_kernel<3>, grid, 256, sizeof(BwdSmem), s, P,
-               reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
-               reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
-               dL_dconic, dL_dopacity, dL_dcolor, masks);
-  }
-  return GSB_OK;
+  return launch_backward_mma(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
+                             dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, masks, nullptr);
 }

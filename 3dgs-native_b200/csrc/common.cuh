@@ -47,6 +47,9 @@ struct gsb_ctx {
   // per-Gaussian internal buffers for gsb_forward / gsb_backward
   int32_t* tiles_touched = nullptr;
   float* dcov3d = nullptr;
+  float* bwd_acc = nullptr;      // [12 n] packed accumulation records of the backward tile kernel
+  float* bwd_acc_stage = nullptr;  // the same for the stage-level gsb_blend_backward (grown on demand)
+  int64_t bwd_acc_cap = 0;
   int32_t* rank_base = nullptr;  // index of a Gaussian's first arrival rank (fused counting pass)
   int64_t n_cap = 0;
   cudaEvent_t ev_count = nullptr;  // recorded behind the read-back of D: the host waits on it, not on the stream
@@ -325,7 +328,15 @@ int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* 
                                  const int32_t* radii, const float* shs, const float* scales, const float* rotations,
                                  const float* cov3Ds, const float* clamped_state, const float* dL_dmean2D,
                                  const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D, float* dL_dshs,
-                                 float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact);
+                                 float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact,
+                                 const float* packed /* may be null: see preprocess_backward_kernel<.., PACKED> */,
+                                 float* dL_dopacity_out);
+// the backward tile kernel accumulating into the packed 12-float records of `packed` (zeroed here)
+int gsb_blend_backward_packed(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const int32_t* ranges,
+                              const int32_t* point_list, const float* points_xy, const float* conic_opacity,
+                              const float* rgb, const float* final_T, const int32_t* n_contrib,
+                              const float* dL_dpixels, float* packed, const int32_t* block_masks);
+bool gsb_blend_backward_uses_packed();
 
 // ---- stage launchers implemented across the .cu files (host side) --------------------------
 int gsb_scan_i32(gsb_ctx* ctx, cudaStream_t s, int64_t n, const int32_t* in, int32_t* out, bool exclusive,

@@ -24,7 +24,11 @@ constexpr int kShStride = 49;
 // (dL_dRGB masked, unit view direction) as two float4 per Gaussian at dL_dshs[8 i] -- for the
 // multi-GPU exchange, which ships 32 bytes per Gaussian and view instead of 192 and expands them on
 // the receiving side with the same gs_sh_basis.
-template <bool COMPACT>
+// PACKED: the tile-stage gradients come as the packed per-Gaussian record the backward tile kernel
+// accumulates into (12 floats: conic a, b, c, opacity | r, g, b, mean2D.x | mean2D.y, -, -, -; see
+// blend_bwd.cu), and this kernel also writes them out in the reference's layouts (dL_dmean2D float[N][3],
+// dL_dconic float[N][4], dL_dcolor float[N][3], dL_dopacity float[N]): those four arrays are then outputs.
+template <bool COMPACT, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 6)
 preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict__ means, const int* __restrict__ radii,
                            const float* __restrict__ shs, const float* __restrict__ scales,
@@ -32,7 +36,8 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
                            const float* __restrict__ clamped_state, const float* __restrict__ dL_dmean2D,
                            const float* __restrict__ dL_dconic, const float* __restrict__ dL_dcolor,
                            float* __restrict__ dL_dmean3D, float* __restrict__ dL_dshs, float* __restrict__ dL_dscale,
-                           float4* __restrict__ dL_drot, float* __restrict__ dL_dcov3D_out) {
+                           float4* __restrict__ dL_drot, float* __restrict__ dL_dcov3D_out,
+                           const float4* __restrict__ packed, float* __restrict__ dL_dopacity_out) {
   __shared__ float s_sh[kThreads * kShStride];
   const int base = blockIdx.x * kThreads;
   const int tid = threadIdx.x;
@@ -46,9 +51,20 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
   const float2 c3a = *reinterpret_cast<const float2*>(cov3Ds + (size_t)il * 6);
   const float2 c3b = *reinterpret_cast<const float2*>(cov3Ds + (size_t)il * 6 + 2);
   const float2 c3c = *reinterpret_cast<const float2*>(cov3Ds + (size_t)il * 6 + 4);
-  const float4 in_dcon = __ldg(reinterpret_cast<const float4*>(dL_dconic) + il);
-  const float in_g0 = dL_dmean2D[3 * il + 0], in_g1 = dL_dmean2D[3 * il + 1];
-  const float in_dcol[3] = {dL_dcolor[3 * il + 0], dL_dcolor[3 * il + 1], dL_dcolor[3 * il + 2]};
+  float4 in_dcon;
+  float in_g0, in_g1, in_dcol[3], in_dopac = 0.0f;
+  if (PACKED) {
+    const float4 q0 = __ldcs(packed + 3 * (size_t)il), q1 = __ldcs(packed + 3 * (size_t)il + 1);
+    in_g1 = __ldcs(reinterpret_cast<const float*>(packed + 3 * (size_t)il + 2));
+    in_dcon = make_float4(q0.x, q0.y, 0.0f, q0.z);
+    in_dopac = q0.w;
+    in_dcol[0] = q1.x, in_dcol[1] = q1.y, in_dcol[2] = q1.z;
+    in_g0 = q1.w;
+  } else {
+    in_dcon = __ldg(reinterpret_cast<const float4*>(dL_dconic) + il);
+    in_g0 = dL_dmean2D[3 * il + 0], in_g1 = dL_dmean2D[3 * il + 1];
+    in_dcol[0] = dL_dcolor[3 * il + 0], in_dcol[1] = dL_dcolor[3 * il + 1], in_dcol[2] = dL_dcolor[3 * il + 2];
+  }
   const float in_cl[3] = {clamped_state[3 * il + 0], clamped_state[3 * il + 1], clamped_state[3 * il + 2]};
   const float4 in_q = __ldg(reinterpret_cast<const float4*>(rots) + il);
   const float in_s0 = scales[3 * il + 0], in_s1 = scales[3 * il + 1], in_s2 = scales[3 * il + 2];
@@ -330,6 +346,14 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
       dL_dscale[3 * i + c] = o_scale[c];
     }
     dL_drot[i] = o_rot;
+    if (PACKED) {   // the reference's layouts: dL_dmean2D (x, y, 0), dL_dconic (a, b, 0, c) -- backward.py:691-706
+      float* m2 = const_cast<float*>(dL_dmean2D) + 3 * (size_t)i;
+      m2[0] = in_g0, m2[1] = in_g1, m2[2] = 0.0f;
+      reinterpret_cast<float4*>(const_cast<float*>(dL_dconic))[i] = in_dcon;
+      float* dc = const_cast<float*>(dL_dcolor) + 3 * (size_t)i;
+      dc[0] = in_dcol[0], dc[1] = in_dcol[1], dc[2] = in_dcol[2];
+      dL_dopacity_out[i] = in_dopac;
+    }
     if (dL_dcov3D_out) {
       float2* o = reinterpret_cast<float2*>(dL_dcov3D_out + (size_t)i * 6);
       o[0] = make_float2(o_dcov[0], o_dcov[1]);
@@ -361,7 +385,7 @@ GSB_API int gsb_preprocess_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame*
                                     float* dL_dcov3D_internal) {
   return gsb_preprocess_backward_impl(ctx, (cudaStream_t)s, f, n, means, radii, shs, scales, rotations, cov3Ds,
                                       clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
-                                      dL_drot, dL_dcov3D_internal, 0);
+                                      dL_drot, dL_dcov3D_internal, 0, nullptr, nullptr);
 }
 
 GSB_API int gsb_preprocess_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n,
@@ -373,14 +397,15 @@ GSB_API int gsb_preprocess_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const
                                                float* dL_dcov3D_internal) {
   return gsb_preprocess_backward_impl(ctx, (cudaStream_t)s, f, n, means, radii, shs, scales, rotations, cov3Ds,
                                       clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs_compact,
-                                      dL_dscale, dL_drot, dL_dcov3D_internal, 1);
+                                      dL_dscale, dL_drot, dL_dcov3D_internal, 1, nullptr, nullptr);
 }
 
 int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
                                  const int32_t* radii, const float* shs, const float* scales, const float* rotations,
                                  const float* cov3Ds, const float* clamped_state, const float* dL_dmean2D,
                                  const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D, float* dL_dshs,
-                                 float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact) {
+                                 float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact,
+                                 const float* packed, float* dL_dopacity_out) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && n >= 0, "gsb_preprocess_backward: bad frame or n");
   if (n == 0) return GSB_OK;
@@ -392,14 +417,16 @@ int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* 
               "gsb_preprocess_backward: dL_dcov3D_internal must be 8-byte aligned");
   FrameK k;
   gsb_make_framek(f, &k);
-  if (sh_compact) {
-    GSB_LAUNCH(ctx, preprocess_backward_kernel<true>, (int)gsb_div_up(n, kThreads), kThreads, 0, s, k, n, means, radii, shs,
-               scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
-               reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal);
-  } else {
-    GSB_LAUNCH(ctx, preprocess_backward_kernel<false>, (int)gsb_div_up(n, kThreads), kThreads, 0, s, k, n, means, radii, shs,
-               scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
-               reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal);
-  }
+  GSB_REQUIRE(ctx, !packed || (gsb_aligned16(packed) && dL_dopacity_out), "gsb_preprocess_backward: bad packed record");
+  const float4* pk = reinterpret_cast<const float4*>(packed);
+#define GSB_PPB_LAUNCH(C, K)                                                                                              \
+  GSB_LAUNCH(ctx, (preprocess_backward_kernel<C, K>), (int)gsb_div_up(n, kThreads), kThreads, 0, s, k, n, means, radii, shs, \
+             scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, \
+             reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal, pk, dL_dopacity_out)
+  if (sh_compact && packed) GSB_PPB_LAUNCH(true, true);
+  else if (sh_compact) GSB_PPB_LAUNCH(true, false);
+  else if (packed) GSB_PPB_LAUNCH(false, true);
+  else GSB_PPB_LAUNCH(false, false);
+#undef GSB_PPB_LAUNCH
   return GSB_OK;
 }

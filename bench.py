@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--tile-sort", type=int, default=0, help="A/B: 0 bitonic per tile, 1 per-tile radix sort")
     ap.add_argument("--bwd-reduce", type=int, default=2, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
+    ap.add_argument("--bwd-packed", type=int, default=1,
+                    help="A/B: 1 = backward tile kernel accumulates into packed records with vector REDs, 0 = nine scalar REDs")
     ap.add_argument("--fuse-sort", type=int, default=0,
                     help="A/B: 1 = the forward tile kernel's CTAs sort their own tile (lists <= 2048), 0 = tile_sort_kernel")
     ap.add_argument("--sh-compact", type=int, default=1,
@@ -298,6 +300,7 @@ def ours(args):
     T.ctx.set_option("bwd_reduce", args.bwd_reduce)
     T.ctx.set_option("tile_sort", args.tile_sort)
     T.ctx.set_option("fuse_sort", args.fuse_sort)
+    T.ctx.set_option("bwd_packed", args.bwd_packed)
 
     def batch(it):   # one view per rank per step, cycling through the poses
         return [(it * world + r) % N_CAMERAS for r in range(world)]

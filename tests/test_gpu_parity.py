@@ -182,6 +182,33 @@ def test_fused_and_separate_tile_sort_give_the_same_bits(gs, n, w, h, smin, smax
         assert torch.equal(outs[0][2][k], outs[1][2][k]), k
 
 
+@pytest.mark.parametrize("hand_masks_on", [True, False])
+def test_backward_scalar_red_path_agrees_with_oracle(gs, oracle, hand_masks_on):
+    """bwd_packed = 0: the tensor-core backward adds its nine sums per Gaussian straight into the reference's four
+    arrays (scalar REDs) instead of the packed 48-byte records of the default path.  Same tolerance."""
+    from gsb200 import _lib
+    n, w, h = 9000, 180, 120
+    _lib.context().set_option("bwd_packed", 0)
+    try:
+        params, cam, target = gs.scene.synthetic_scene(n, w, h, 0.005, 0.08, seed=77)
+        kw = gs.scene.render_kwargs(params, cam, background=(0.1, 0.3, 0.7))
+        got = gs.forward.render_gaussians(**kw)
+        oracle.set_threads(oracle.max_threads())
+        want = oracle.render_gaussians(**kw)
+        check_forward(got, want)
+        dpix = np.random.default_rng(5).normal(size=(h, w, 3)).astype(np.float32)
+        buffers = dict(got[2])
+        if not hand_masks_on:
+            del buffers["block_masks"]
+        grads = gs.backward.backward(**gs.scene.backward_kwargs(params, cam, buffers, dpix, background=(0.1, 0.3, 0.7)))
+        oracle.set_threads(1)
+        ograds = oracle.backward(**gs.scene.backward_kwargs(params, cam, want[2], dpix, background=(0.1, 0.3, 0.7)))
+        check_grads(grads, ograds)
+    finally:
+        oracle.set_threads(1)
+        _lib.context().set_option("bwd_packed", 1)
+
+
 def test_backward_writes_into_caller_buffers(gs):
     """backward(out=...) (our extension): results land in the given tensors, the others are allocated."""
     params, cam, target = gs.scene.synthetic_scene(3000, 96, 64, 0.01, 0.1, seed=3)

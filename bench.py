@@ -382,19 +382,20 @@ def ours(args):
         def e2e_step(it, pending=None):
             ci = batch(it)[rank]
             cam = cams[ci]
-            img, _depth, buf = gf.render_gaussians(**scene.render_kwargs(P.as_dict(), cam, background=bg))
-            if pending is not None:
-                consume(pending)                     # the previous step's loss (its copy finished long ago)
-            # H2D of the step's input from pinned memory, on a copy stream, issued as soon as the forward
-            # call returns (its tile kernel is still running): the forward does not read the target, so
-            # the 7.7 MB transfer (~150 us over PCIe) runs beside it; the loss kernel waits for it.
-            # Two device buffers, reused: the forward call's host wait (on D) is behind every earlier step
-            # in the stream, so by now the step that last read this buffer has completed.
+            # H2D of the step's input from pinned memory, on a copy stream, issued FIRST: the forward does not read
+            # the target, so the 7.7 MB transfer (150-300 us over PCIe, depending on the box) runs beside the tail
+            # of the previous step and this step's forward; the loss kernel waits for it.  Two device buffers,
+            # reused: buffer it & 1 was last read by the loss kernel of step it - 2, and the forward call of step
+            # it - 1 has returned, i.e. its host wait (behind preprocess of it - 1 in the stream, hence behind all
+            # of step it - 2) is over.
             main = torch.cuda.current_stream()
             tgt, ready = tgt_dev[it & 1], tgt_ready[it & 1]
             with torch.cuda.stream(copy_stream):
                 tgt.copy_(pinned[ci], non_blocking=True)
                 ready.record(copy_stream)
+            img, _depth, buf = gf.render_gaussians(**scene.render_kwargs(P.as_dict(), cam, background=bg))
+            if pending is not None:
+                consume(pending)                     # the previous step's loss (its copy finished long ago)
             main.wait_event(ready)
             loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0)
             if world > 1:

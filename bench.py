@@ -474,11 +474,11 @@ def ours(args):
                     "note": "the tile kernels are instruction-issue bound and their working set sits in L2 (DRAM traffic "
                             "below the algorithmic bytes), so the HBM fraction of the kernel with the largest share "
                             "of the step is small by nature; issue-slot utilisation and per-kernel ncu summaries: "
-                            "profiles/r01_ncu_blend_v10.md",
+                            "profiles/r01_ncu_blend_v12.md",
                     # what does bound that kernel, from the committed ncu captures (not measured by this run)
-                    "limiters_from_ncu": {"issue_slots_frac": 0.63, "lsu_data_pipe_wavefronts_frac": 0.76,
-                                          "tensor_pipe_frac": 0.19, "dram_frac": 0.02,
-                                          "source": "profiles/r01_ncu_blend_v10.md, profiles/r01_ncu_bwd_warp_autonomous.md"}}
+                    "limiters_from_ncu": {"issue_slots_frac": 0.665, "lsu_data_pipe_wavefronts_frac": 0.65,
+                                          "tensor_pipe_frac": 0.20, "dram_frac": 0.02,
+                                          "source": "profiles/r01_ncu_blend_v12.md"}}
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N=1 only) ----------------
     cpu = None

@@ -43,6 +43,14 @@ def shard_views(batch, rank: int, world_size: int):
     return list(batch[rank * per:(rank + 1) * per])
 
 
+def compact_sh_step(enabled: bool, num_views: int, world_size: int) -> bool:
+    """Whether a step's SH gradients can cross NVLink as their rank-1 factors (gsb_backward_compact_sh +
+    gsb_adam_step_peers_compact): only when every rank renders exactly ONE view -- the factors of two views
+    do not add -- and there is somebody to exchange with.  A function of global quantities only, so all
+    ranks decide alike."""
+    return bool(enabled) and world_size > 1 and num_views == world_size
+
+
 def flat_layout(n: int):
     """Offsets (in floats) of the five tensors inside a FlatGaussians buffer and its total length:
     every segment starts on a 16-byte boundary."""
@@ -362,7 +370,7 @@ class Trainer:
         sum|render - target| (divide by 3HW for the reference's loss)."""
         mine = shard_views(list(range(len(cam_indices))), self.rank, self.world_size)
         # one view on every rank: the SH gradient can travel as its rank-1 factors (same on all ranks)
-        self._compact_step = self.sh_compact and len(cam_indices) == self.world_size
+        self._compact_step = compact_sh_step(self.sh_compact, len(cam_indices), self.world_size)
         fb = None
         for j, b in enumerate(mine):
             ci = cam_indices[b]

@@ -102,3 +102,15 @@ def test_shard_views_rejects_ragged_batches():
         train.shard_views([1, 2, 3], 0, 2)
     offs, total = train.flat_layout(5)
     assert offs["positions"] == 0 and all(o % 4 == 0 for o in offs.values()) and total >= 59 * 5
+
+
+def test_compact_sh_exchange_only_with_one_view_per_rank():
+    """The rank-1 form of the SH gradient is valid for ONE view: every rank must take the same decision from
+    global quantities (batch size, world size)."""
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import gsb200  # noqa: F401
+    from gsb200 import train
+    assert train.compact_sh_step(True, 4, 4) and train.compact_sh_step(True, 2, 2)
+    assert not train.compact_sh_step(True, 8, 4)       # two views per rank: factors do not add
+    assert not train.compact_sh_step(True, 1, 1)       # nobody to exchange with
+    assert not train.compact_sh_step(False, 4, 4)

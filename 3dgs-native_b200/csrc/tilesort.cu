@@ -61,12 +61,22 @@ tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__
   if (tid == 0) s_carry = 0;
   int my_max = 0;
   __syncthreads();
-  for (int base = 0; base < num_tiles; base += 1024) {
-    const int i = base + tid;
-    const int c = (i < num_tiles) ? tile_count[(size_t)i * kCntStride] : 0;
-    if (c != 0) tile_count[(size_t)i * kCntStride] = 0;
-    my_max = max(my_max, c);
-    int inc = c;
+  // four consecutive tiles per thread, all four counters (one 128-byte line each) requested before the scan:
+  // 4096 tiles per round -- one round at 800x800, where the chain of dependent loads used to cost three
+  constexpr int kPer = 4;
+  for (int base = 0; base < num_tiles; base += 1024 * kPer) {
+    const int i0 = base + tid * kPer;
+    int c[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) c[k] = (i0 + k < num_tiles) ? tile_count[(size_t)(i0 + k) * kCntStride] : 0;
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (c[k] != 0) tile_count[(size_t)(i0 + k) * kCntStride] = 0;
+      my_max = max(my_max, c[k]);
+      local += c[k];
+    }
+    int inc = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -81,9 +91,11 @@ tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__
       if (w < warp) wb += t;
       tot += t;
     }
-    const int start = s_carry + wb + inc - c;
-    if (i < num_tiles) {
-      ranges[i] = (c > 0) ? make_int2(start, start + c) : make_int2(0, 0);
+    int start = s_carry + wb + inc - local;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (i0 + k < num_tiles) ranges[i0 + k] = (c[k] > 0) ? make_int2(start, start + c[k]) : make_int2(0, 0);
+      start += c[k];
     }
     __syncthreads();
     if (tid == 0) s_carry += tot;

@@ -257,6 +257,86 @@ __device__ __forceinline__ void mma_tf32_k4(float d[4], float a0, float a1, floa
 
 __device__ __forceinline__ float f4_get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
 
+// The tensor-core part of a group flush, shared by the two tensor-core kernels: the warp's S / W tiles (kGrp hits
+// x 32 pixels) times the constant pixel matrices.  On return lane l (and l + 16) holds, for the group's hit
+// l & 15, the six moments  sum_p s * {1, i, r, i^2, i r, r^2}  (m03, m45) and the three colour sums
+// sum_p w * dL_dpixel[p][c]  (col); the S tile is used as scratch for the results.
+__device__ __forceinline__ void bwd_group_moments(float* tS, const float* tW, const int lane, const int fg, const int ft,
+                                                  const float m0, const float m1, const float m2, const float* dp_row,
+                                                  const int dp_cols, float4& m03, float2& m45, float4& col) {
+  __syncwarp();
+  float dm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  // k-step ks (m16n8k4) covers the pixels (i = ks, r = 0..3); lane (fg, ft) supplies rows fg, fg + 8
+  // at pixel 8 ft + ks: two float4 per half row serve four k-steps.
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float4 va = *reinterpret_cast<const float4*>(tS + fg * kSRow + 8 * ft + 4 * half);
+    const float4 vb = *reinterpret_cast<const float4*>(tS + (fg + 8) * kSRow + 8 * ft + 4 * half);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ks = (float)(4 * half + e);
+      const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
+      const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
+      const float b0 = m0 + ks * (m1 + ks * m2);
+      mma_tf32_k4(dm, h0, h1, b0);
+      mma_tf32_k4(dm, a0 - h0, a1 - h1, b0);
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float4 va = *reinterpret_cast<const float4*>(tW + fg * kSRow + 8 * ft + 4 * half);
+    const float4 vb = *reinterpret_cast<const float4*>(tW + (fg + 8) * kSRow + 8 * ft + 4 * half);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 4 * half + e;
+      const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
+      const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
+      const float dpv = (i < dp_cols) ? __ldg(dp_row + 3 * i) : 0.0f;
+      const float p0 = tf32_hi(dpv);
+      mma_tf32_k4(dc, h0, h1, p0);
+      mma_tf32_k4(dc, a0 - h0, a1 - h1, p0);
+      mma_tf32_k4(dc, h0, h1, dpv - p0);
+    }
+  }
+  __syncwarp();  // every lane has read its operands: the S tile may now take the results
+  *reinterpret_cast<float2*>(tS + fg * kDRow + 2 * ft) = make_float2(dm[0], dm[1]);
+  *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 2 * ft) = make_float2(dm[2], dm[3]);
+  if (ft < 2) {
+    *reinterpret_cast<float2*>(tS + fg * kDRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
+    *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
+  }
+  __syncwarp();
+  m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow);
+  m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kDRow + 4);
+  col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow + 8);
+}
+
+// a hit none of the 32 pixels used sums to nine exact zeros: adding them would be a no-op
+__device__ __forceinline__ bool bwd_group_nonzero(const float4& m03, const float2& m45, const float4& col) {
+  return ((__float_as_uint(m03.x) | __float_as_uint(m03.y) | __float_as_uint(m03.z) | __float_as_uint(m03.w) |
+           __float_as_uint(m45.x) | __float_as_uint(m45.y) | __float_as_uint(col.x) | __float_as_uint(col.y) |
+           __float_as_uint(col.z)) << 1) != 0u;
+}
+
+// The moments of one hit (ga = x, y, conic.a, conic.c; gb = conic.b, opacity, ..; block origin bx0, by0) turned
+// into its gradients (backward.py:683-706): g[0..2] dL_dconic a, b, c; g[3] dL_dmean2D x; g[4] dL_dmean2D y.
+// dL_dopacity is m03.x, dL_dcolor is col.
+__device__ __forceinline__ void bwd_group_gradients(const float4& ga, const float4& gb, const float bx0f, const float by0f,
+                                                    const float4& m03, const float2& m45, const float ddelx_dx,
+                                                    const float ddely_dy, float g[5]) {
+  const float ux = ga.x - bx0f, uy = ga.y - by0f;   // dx = ux - i, dy = uy - r
+  const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
+  const float Sdx = ux * S0 - Si;
+  const float Sdy = uy * S0 - Sr;
+  const float Sdxx = ux * (Sdx - Si) + Sii;
+  const float Sdxy = ux * Sdy - uy * Si + Sir;
+  const float Sdyy = uy * (Sdy - Sr) + Srr;
+  const float o = gb.y;  // dL_dG = opacity * dL_dalpha (backward.py:683)
+  g[3] = -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx;   // backward.py:691-695
+  g[4] = -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy;
+  g[0] = -0.5f * o * Sdxx, g[1] = -0.5f * o * Sdxy, g[2] = -0.5f * o * Sdyy;   // backward.py:698-703
+}
+
 // 16-byte vector reduction (sm_90+): four float adds at one 16-byte-aligned address in ONE instruction and one
 // L2 sector operation (REDG.E.ADD.F32x4, same FTZ.RN flavour as the scalar RED atomicAdd compiles to).
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -390,86 +470,29 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     // Group of `count` hits complete (rows 0 .. count-1 of the tiles, list entries qbase ..): reduce
     // them over the 32 pixels on the tensor cores and add the results to the gradient arrays.
     auto flush_group = [&](const int qbase, const int count) {
-      __syncwarp();
-      float dm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      // k-step ks (m16n8k4) covers the pixels (i = ks, r = 0..3); lane (fg, ft) supplies rows fg, fg + 8
-      // at pixel 8 ft + ks: two float4 per half row serve four k-steps.
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float4 va = *reinterpret_cast<const float4*>(tS + fg * kSRow + 8 * ft + 4 * half);
-        const float4 vb = *reinterpret_cast<const float4*>(tS + (fg + 8) * kSRow + 8 * ft + 4 * half);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float ks = (float)(4 * half + e);
-          const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
-          const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
-          const float b0 = m0 + ks * (m1 + ks * m2);
-          mma_tf32_k4(dm, h0, h1, b0);
-          mma_tf32_k4(dm, a0 - h0, a1 - h1, b0);
-        }
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float4 va = *reinterpret_cast<const float4*>(tW + fg * kSRow + 8 * ft + 4 * half);
-        const float4 vb = *reinterpret_cast<const float4*>(tW + (fg + 8) * kSRow + 8 * ft + 4 * half);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = 4 * half + e;
-          const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
-          const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
-          const float dpv = (i < dp_cols) ? __ldg(dp_row + 3 * i) : 0.0f;
-          const float p0 = tf32_hi(dpv);
-          mma_tf32_k4(dc, h0, h1, p0);
-          mma_tf32_k4(dc, a0 - h0, a1 - h1, p0);
-          mma_tf32_k4(dc, h0, h1, dpv - p0);
-        }
-      }
-      __syncwarp();  // every lane has read its operands: the S tile may now take the results
-      *reinterpret_cast<float2*>(tS + fg * kDRow + 2 * ft) = make_float2(dm[0], dm[1]);
-      *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 2 * ft) = make_float2(dm[2], dm[3]);
-      if (ft < 2) {
-        *reinterpret_cast<float2*>(tS + fg * kDRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
-        *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
-      }
-      __syncwarp();
-      const float4 m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow);
-      const float2 m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kDRow + 4);
-      const float4 col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow + 8);
-      // a hit none of the 32 pixels used sums to nine exact zeros: adding them would be a no-op
-      const unsigned nz = (__float_as_uint(m03.x) | __float_as_uint(m03.y) | __float_as_uint(m03.z) |
-                           __float_as_uint(m03.w) | __float_as_uint(m45.x) | __float_as_uint(m45.y) |
-                           __float_as_uint(col.x) | __float_as_uint(col.y) | __float_as_uint(col.z)) << 1;
-      if (lane < count && nz != 0u) {
+      float4 m03, col;
+      float2 m45;
+      bwd_group_moments(tS, tW, lane, fg, ft, m0, m1, m2, dp_row, dp_cols, m03, m45, col);
+      if (lane < count && bwd_group_nonzero(m03, m45, col)) {
         const int je = wlist[qbase + lane];
-        const float4 ga = sm.a[je];   // x, y, conic.a, conic.c
-        const float4 gb = sm.b[je];   // conic.b, opacity, ..
         const int gid = __float_as_int(sm.c[je].w);
-        const float ux = ga.x - (float)bx0, uy = ga.y - (float)by0;   // dx = ux - i, dy = uy - r
-        const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
-        const float Sdx = ux * S0 - Si;
-        const float Sdy = uy * S0 - Sr;
-        const float Sdxx = ux * (Sdx - Si) + Sii;
-        const float Sdxy = ux * Sdy - uy * Si + Sir;
-        const float Sdyy = uy * (Sdy - Sr) + Srr;
-        const float o = gb.y;  // dL_dG = opacity * dL_dalpha (backward.py:683)
-        const float gmx = -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx;   // backward.py:691-695
-        const float gmy = -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy;
-        const float gca = -0.5f * o * Sdxx, gcb = -0.5f * o * Sdxy, gcc = -0.5f * o * Sdyy;   // backward.py:698-703
+        float g[5];
+        bwd_group_gradients(sm.a[je], sm.b[je], (float)bx0, (float)by0, m03, m45, ddelx_dx, ddely_dy, g);
         if (PACKED) {
           float* const rec = acc_packed + 12 * (size_t)gid;
-          red_add_v4(rec, gca, gcb, gcc, S0);
-          red_add_v4(rec + 4, col.x, col.y, col.z, gmx);
-          atomicAdd(rec + 8, gmy);
+          red_add_v4(rec, g[0], g[1], g[2], m03.x);
+          red_add_v4(rec + 4, col.x, col.y, col.z, g[3]);
+          atomicAdd(rec + 8, g[4]);
         } else {
           atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
           atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
           atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
-          atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, gmx);
-          atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, gmy);
-          atomicAdd(dL_dconic + 4 * (size_t)gid + 0, gca);
-          atomicAdd(dL_dconic + 4 * (size_t)gid + 1, gcb);
-          atomicAdd(dL_dconic + 4 * (size_t)gid + 3, gcc);
-          atomicAdd(dL_dopacity + gid, S0);   // backward.py:706
+          atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, g[3]);
+          atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, g[4]);
+          atomicAdd(dL_dconic + 4 * (size_t)gid + 0, g[0]);
+          atomicAdd(dL_dconic + 4 * (size_t)gid + 1, g[1]);
+          atomicAdd(dL_dconic + 4 * (size_t)gid + 3, g[2]);
+          atomicAdd(dL_dopacity + gid, m03.x);   // backward.py:706
         }
       }
       __syncwarp();  // results consumed before the next group overwrites the tile
@@ -617,74 +640,23 @@ blend_backward_warp_kernel(const BlendParams P, const int2* __restrict__ ranges,
 
   // the open group's hits are the ring entries gbase .. gbase + count - 1
   auto flush_group = [&](const int gbase, const int count) {
-    __syncwarp();
-    float dm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const float4 va = *reinterpret_cast<const float4*>(tS + fg * kSRow + 8 * ft + 4 * half);
-      const float4 vb = *reinterpret_cast<const float4*>(tS + (fg + 8) * kSRow + 8 * ft + 4 * half);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float ks = (float)(4 * half + e);
-        const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
-        const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
-        const float b0 = m0 + ks * (m1 + ks * m2);
-        mma_tf32_k4(dm, h0, h1, b0);
-        mma_tf32_k4(dm, a0 - h0, a1 - h1, b0);
-      }
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const float4 va = *reinterpret_cast<const float4*>(tW + fg * kSRow + 8 * ft + 4 * half);
-      const float4 vb = *reinterpret_cast<const float4*>(tW + (fg + 8) * kSRow + 8 * ft + 4 * half);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = 4 * half + e;
-        const float a0 = f4_get(va, e), a1 = f4_get(vb, e);
-        const float h0 = tf32_hi(a0), h1 = tf32_hi(a1);
-        const float dpv = (i < dp_cols) ? __ldg(dp_row + 3 * i) : 0.0f;
-        const float p0 = tf32_hi(dpv);
-        mma_tf32_k4(dc, h0, h1, p0);
-        mma_tf32_k4(dc, a0 - h0, a1 - h1, p0);
-        mma_tf32_k4(dc, h0, h1, dpv - p0);
-      }
-    }
-    __syncwarp();
-    *reinterpret_cast<float2*>(tS + fg * kDRow + 2 * ft) = make_float2(dm[0], dm[1]);
-    *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 2 * ft) = make_float2(dm[2], dm[3]);
-    if (ft < 2) {
-      *reinterpret_cast<float2*>(tS + fg * kDRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
-      *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
-    }
-    __syncwarp();
-    const float4 m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow);
-    const float2 m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kDRow + 4);
-    const float4 col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow + 8);
-    const unsigned nz = (__float_as_uint(m03.x) | __float_as_uint(m03.y) | __float_as_uint(m03.z) |
-                         __float_as_uint(m03.w) | __float_as_uint(m45.x) | __float_as_uint(m45.y) |
-                         __float_as_uint(col.x) | __float_as_uint(col.y) | __float_as_uint(col.z)) << 1;
-    if (lane < count && nz != 0u) {
+    float4 m03, col;
+    float2 m45;
+    bwd_group_moments(tS, tW, lane, fg, ft, m0, m1, m2, dp_row, dp_cols, m03, m45, col);
+    if (lane < count && bwd_group_nonzero(m03, m45, col)) {
       const int je = (gbase + lane) & 63;
-      const float4 ga = sm.a[je];
-      const float4 gb = sm.b[je];
       const int gid = __float_as_int(sm.c[je].w);
-      const float ux = ga.x - (float)bx0, uy = ga.y - (float)by0;
-      const float S0 = m03.x, Si = m03.y, Sr = m03.z, Sii = m03.w, Sir = m45.x, Srr = m45.y;
-      const float Sdx = ux * S0 - Si;
-      const float Sdy = uy * S0 - Sr;
-      const float Sdxx = ux * (Sdx - Si) + Sii;
-      const float Sdxy = ux * Sdy - uy * Si + Sir;
-      const float Sdyy = uy * (Sdy - Sr) + Srr;
-      const float o = gb.y;
+      float g[5];
+      bwd_group_gradients(sm.a[je], sm.b[je], (float)bx0, (float)by0, m03, m45, ddelx_dx, ddely_dy, g);
       atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
       atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
       atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
-      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, -o * (ga.z * Sdx + gb.x * Sdy) * ddelx_dx);
-      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, -o * (ga.w * Sdy + gb.x * Sdx) * ddely_dy);
-      atomicAdd(dL_dconic + 4 * (size_t)gid + 0, -0.5f * o * Sdxx);
-      atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * o * Sdxy);
-      atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * o * Sdyy);
-      atomicAdd(dL_dopacity + gid, S0);
+      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, g[3]);
+      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, g[4]);
+      atomicAdd(dL_dconic + 4 * (size_t)gid + 0, g[0]);
+      atomicAdd(dL_dconic + 4 * (size_t)gid + 1, g[1]);
+      atomicAdd(dL_dconic + 4 * (size_t)gid + 3, g[2]);
+      atomicAdd(dL_dopacity + gid, m03.x);
     }
     __syncwarp();
     gslot = 0;

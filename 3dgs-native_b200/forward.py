@@ -71,6 +71,8 @@ def render_gaussians(background, means3D, colors=None, opacity=None, scales=None
     out["point_list"] = point_list[: int(D.value)]
     res = {k: out[k] for k in _KEYS}
     # not a reference key: the tile kernels' per-entry culling masks; backward() reuses them when the
-    # dict is passed on as binning_buffer, and recomputes them when the key is absent
+    # dict is passed on as binning_buffer, and recomputes them when the key is absent.  Entries behind the
+    # point where a tile's last pixel terminated are never staged by the forward: their masks stay unwritten,
+    # and the backward (which replays at most n_contrib entries per pixel) never reads them
     res["block_masks"] = block_masks[: int(D.value)]
     return image, depth, res

@@ -179,6 +179,8 @@ def test_fused_and_separate_tile_sort_give_the_same_bits(gs, n, w, h, smin, smax
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert outs[0][2]["point_list"].numel() > 0
     for k in outs[0][2]:
+        if k == "block_masks":
+            continue   # entries behind a tile's early exit are never staged: their masks stay unwritten (and unread)
         assert torch.equal(outs[0][2][k], outs[1][2][k]), k
 
 

@@ -11,7 +11,9 @@ iteration:
   half lists    two independent lists per warp, one per 16-lane half: iterations = max over the halves
   quarter lists four lists per warp: iterations = max over the four quarters
 
-    python tools/block_layout_study.py [--tiles 400]
+    python tests/studies/block_layout_study.py [--tiles 400]
+
+(It lives under tests/ because it drives the CPU oracle, which is test infrastructure.)
 
 prints a table; the numbers quoted in DESIGN.md come from this script.
 """
@@ -21,7 +23,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)

@@ -158,3 +158,24 @@ def test_ssim_and_depth_loss_match_reference_source(golden_dir):
     assert abs(O.ssim(g["rendered"], g["target"]) - float(g["ssim"])) <= 1e-6
     assert abs(O.ssim(g["rendered"], g["rendered"]) - 1.0) <= 1e-6 and abs(float(g["ssim_same"]) - 1.0) <= 1e-6
     assert abs(O.depth_loss(g["rendered_depth"], g["target_depth"], g["depth_mask"]) - float(g["depth_loss"])) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["ref_example_96", "ref_lego_bg", "ref_lego_small"])
+def test_reference_sh_gradient_is_rank_one(golden_dir, name):
+    """What the compact multi-GPU exchange relies on, checked on the REFERENCE's own
+    backward output (goldens recorded from its unmodified source): for one view the 16 x 3 SH gradient of a
+    Gaussian is the outer product basis(dir) x dL_dRGB (backward.py:116-213) -- rank one up to fp32
+    rounding -- and its DC row is exactly SH_C0 * dL_dcolor * (1 - clamped_state) in binary32."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sh = g["bwd_dL_dshs"].reshape(-1, 16, 3)
+    live = 0
+    for m in sh.astype(np.float64):
+        s = np.linalg.svd(m, compute_uv=False)
+        if s[0] > 0:
+            live += 1
+            assert s[1] <= 1e-6 * s[0]
+    assert live >= 3
+    drgb = (g["bwd_dL_dcolor"].astype(np.float32) * (np.float32(1.0) + np.float32(-1.0) * g["fwd_clamped_state"].astype(np.float32)))
+    dc = (np.float32(0.28209479177387814) * drgb).astype(np.float32)
+    wrote = np.abs(sh).sum(axis=(1, 2)) > 0          # Gaussians the SH backward skipped keep zeros
+    assert np.array_equal(sh[wrote, 0, :], dc[wrote])

@@ -1,8 +1,8 @@
-// blend.cu -- the per-16x16-tile alpha blend and its back-to-front backward.
-//   blend_forward_kernel  replaces wp_render_gaussians      (forward.py:384-515)
-//   blend_backward_kernel replaces wp_render_backward_kernel (backward.py:558-706)
+// blend.cu -- the per-16x16-tile alpha blend.  Its back-to-front backward lives in blend_bwd.cu.
+//   blend_forward_kernel   replaces wp_render_gaussians       (forward.py:384-515)
+//   blend_backward_* (blend_bwd.cu) replace wp_render_backward_kernel (backward.py:558-706)
 //
-// Design (both kernels): one CTA per tile, 256 threads, one pixel per thread; a warp owns a 4x8
+// Design (forward and backward): one CTA per tile, 256 threads, one pixel per thread; a warp owns a 4x8
 // pixel block (blend_common.cuh), so per-pixel loads/stores are 32-byte row segments (the
 // reference's launch maps adjacent lanes to a pixel COLUMN).  The tile's depth-sorted Gaussians
 // are staged through shared memory in batches of 256 (one gather per Gaussian per tile instead of
@@ -22,10 +22,10 @@
 // bit-identical to the oracle: culling only ever removes pairs the reference would `continue` on.
 // Forward: a CTA stops as soon as every one of its pixels has terminated (__syncthreads_and).
 //
-// Backward: the reference issues 11 scalar global atomics per (pixel, Gaussian) pair.  Here the
-// warp reduces the nine live gradient scalars with a transposed butterfly (9 + 5 shuffles instead of
-// 45), and nine lanes issue one RED each per (warp, Gaussian) -- and only for Gaussians that
-// touched the warp at all.
+// Backward (blend_bwd.cu): the reference issues 11 scalar global atomics per (pixel, Gaussian) pair.
+// There a warp sums its pixels' terms for 16 Gaussians at a time on the tensor cores and adds the nine
+// results per Gaussian to one packed record with two vector REDs and a scalar one -- and only for
+// Gaussians that touched the warp at all.
 #include <type_traits>
 
 #include "blend_common.cuh"

@@ -53,11 +53,12 @@ _SIGS = {
     "gsb_adam_step": (C.c_int, [vp, vp, i32] + [vp] * 5 + [f32] * 8 + [i32] + [vp] * 15),
     "gsb_flat_layout": (C.c_int, [i32, C.POINTER(i64), C.POINTER(i64)]),
     "gsb_adam_step_peers": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64,
-                                      C.c_uint64, vp, vp] + [f32] * 8 + [i32]),
+                                      C.c_uint64, vp, vp] + [f32] * 8 + [i32, i32]),
     "gsb_adam_step_peers_compact": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
-                                              C.c_uint64, vp, vp] + [f32] * 8 + [i32, vp, i64, i32]),
+                                              C.c_uint64, vp, vp] + [f32] * 8 + [i32, vp, i64, i32, i32]),
     "gsb_fill_f32": (C.c_int, [vp, vp, vp, i64, f32]),
     "gsb_selftest_block_mask": (C.c_int, [vp, vp, i32, vp, vp, vp]),
+    "gsb_selftest_work_counters": (C.c_int, [vp, vp, C.POINTER(Frame)] + [vp] * 6),
     "gsb_selftest_div": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, vp]),
     "gsb_accumulate_f32": (C.c_int, [vp, vp, vp, vp, i64]),
     "gsb_init_gaussian_params": (C.c_int, [vp, vp, i32, f32] + [vp] * 5),

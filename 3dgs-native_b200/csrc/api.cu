@@ -25,13 +25,7 @@ int gsb_blend_forward_sorting(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, 
                               const unsigned long long* binned, int32_t* point_list, const float* points_xy,
                               const float* rgb, const float* conic_opacity, const float* depths, float* image,
                               float* inv_depth, float* final_T, int32_t* n_contrib, int32_t* block_masks);
-int gsb_blend_forward_fused_sort_max();
-int g_fuse_sort = 0;  // 1 (A/B): tiles of up to 2048 entries are sorted by the forward tile kernel's own CTAs -- measured slower
-int g_binning = 0;  // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
-int g_blend_cull = 1;
-int g_tile_sort = 0;   // 0: bitonic network for every tile (default); 1: per-tile LSD radix sort (bitonic for tiles > 4096)
-int g_bwd_reduce = 2;
-int g_bwd_packed = 1;  // 1: tensor-core backward accumulates into packed records with vector REDs (default); 0: nine scalar REDs
+int gsb_blend_forward_fused_sort_max(const gsb_ctx* ctx);
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -159,29 +153,29 @@ GSB_API int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered) {
 
 // A/B knobs (not part of the reference surface; results never depend on them)
 GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
-  if (!name) return GSB_ERR_INVALID;
+  if (!name || !ctx) return GSB_ERR_INVALID;
   if (!strcmp(name, "binning") && (value == 0 || value == 1)) {
-    g_binning = value;
+    ctx->opt.binning = value;
     return GSB_OK;
   }
   if (!strcmp(name, "blend_cull") && (value == 0 || value == 1)) {
-    g_blend_cull = value;
+    ctx->opt.blend_cull = value;
     return GSB_OK;
   }
   if (!strcmp(name, "tile_sort") && (value == 0 || value == 1)) {
-    g_tile_sort = value;
+    ctx->opt.tile_sort = value;
     return GSB_OK;
   }
   if (!strcmp(name, "bwd_packed") && (value == 0 || value == 1)) {
-    g_bwd_packed = value;
+    ctx->opt.bwd_packed = value;
     return GSB_OK;
   }
   if (!strcmp(name, "fuse_sort") && (value == 0 || value == 1)) {
-    g_fuse_sort = value;
+    ctx->opt.fuse_sort = value;
     return GSB_OK;
   }
-  if (!strcmp(name, "bwd_reduce") && value >= 0 && value <= 4) {
-    g_bwd_reduce = value;
+  if (!strcmp(name, "bwd_reduce") && value >= 0 && value <= 2) {
+    ctx->opt.bwd_reduce = value;
     return GSB_OK;
   }
   return gsb_set_error(ctx, GSB_ERR_INVALID, "unknown option %s=%d", name, value);
@@ -223,7 +217,7 @@ GSB_API int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s_, int32_t width, int32_t 
                          (long long)point_list_capacity, (long long)D);
 
   if (D == 0) return GSB_OK;  // ranges are all (0,0) already
-  if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
+  if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
     // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
     rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, point_offsets, 0, ranges, D,
                                max_count, point_list);
@@ -292,13 +286,13 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
                          (long long)point_list_capacity, (long long)D);
   bool sort_in_blend = false;
   if (D > 0) {
-    if (g_binning == 0 && max_count <= gsb_blend_forward_fused_sort_max()) {
+    if (ctx->opt.binning == 0 && max_count <= gsb_blend_forward_fused_sort_max(ctx)) {
       // scatter only: every CTA of the forward tile kernel sorts its own tile first
       rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ctx->rank_base, 1, ranges, D,
                                  max_count, nullptr);
       if (rc != GSB_OK) return rc;
       sort_in_blend = true;
-    } else if (g_binning == 0 && max_count <= gsb_tile_binning_max()) {
+    } else if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
       // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
       rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ctx->rank_base, 1, ranges, D,
                                  max_count, point_list);
@@ -346,7 +340,7 @@ static int backward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_
   if ((rc = reserve_per_gaussian(ctx, s, n)) != GSB_OK) return rc;
   // backward.py:1135-1152.  Default: the tile kernel accumulates into packed per-Gaussian records (vector REDs)
   // and the per-Gaussian pass writes dL_dmean2D / dL_dconic / dL_dcolor / dL_dopacity out in the reference's layouts.
-  const bool packed = gsb_blend_backward_uses_packed();
+  const bool packed = gsb_blend_backward_uses_packed(ctx);
   if (packed)
     rc = gsb_blend_backward_packed(ctx, s, f, n, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
                                    dL_dpixels, ctx->bwd_acc, block_masks);

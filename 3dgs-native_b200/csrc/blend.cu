@@ -31,7 +31,6 @@
 #include "blend_common.cuh"
 #include "tilesort.cuh"
 
-extern int g_fuse_sort;
 
 namespace {
 
@@ -232,7 +231,7 @@ int gsb_blend_forward_sorting(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, 
   GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0, "gsb_blend_forward: bad frame");
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_forward: conic_opacity must be 16-byte aligned");
   static_assert(sizeof(FwdSmem) >= kFusedSortMax * sizeof(unsigned long long), "the sort buffer aliases the staging arrays");
-  BlendParams P = make_blend_params(f);
+  BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
   GSB_LAUNCH(ctx, blend_forward_kernel<true>, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
              point_list, binned, reinterpret_cast<const float2*>(points_xy), rgb,
@@ -240,7 +239,7 @@ int gsb_blend_forward_sorting(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, 
              reinterpret_cast<unsigned*>(block_masks));
   return GSB_OK;
 }
-int gsb_blend_forward_fused_sort_max() { return g_fuse_sort ? kFusedSortMax : 0; }
+int gsb_blend_forward_fused_sort_max(const gsb_ctx* ctx) { return ctx->opt.fuse_sort ? kFusedSortMax : 0; }
 
 GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* rgb,
@@ -250,7 +249,7 @@ GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, c
   GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0, "gsb_blend_forward: bad frame");
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_forward: conic_opacity must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)s_;
-  BlendParams P = make_blend_params(f);
+  BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
   GSB_LAUNCH(ctx, blend_forward_kernel<false>, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
              point_list, nullptr, reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity), depths,

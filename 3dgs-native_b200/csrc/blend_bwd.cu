@@ -221,13 +221,28 @@ struct BwdSmem {
 // sm_100a).  x - tf32_hi(x) is exact, so hi + lo carries >= 20 mantissa bits through the MMA.
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// exp(x) for x <= 0 on the MUFU unit (2 ulp).  The backward's alpha only feeds tolerance-compared
-// gradients; its one decision (alpha < 1/255) can differ from the forward's for a pair within a few
-// ulp of the threshold, which changes that pixel's replayed T by 0.4% -- about one pair in 1e6.
+// exp(x) for x <= 0 on the MUFU unit (2 ulp; with the rounding of x * log2(e), < 6e-7 relative for
+// the exponents that pass the threshold test).  The backward's alpha VALUE only feeds tolerance-compared
+// gradients.
 __device__ __forceinline__ float exp_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
   return r;
+}
+
+// The backward's alpha and its one DECISION, alpha >= 1/255 (backward.py:655), which must be the
+// forward's (forward.py:479): a pair the two passes disagree on would replay a different T for the rest
+// of that pixel.  The MUFU value decides unless it lies within 1e-7 (2.5e-5 relative, forty times the
+// MUFU error bound) of the threshold; those pairs -- about one in 1e5 -- are decided with the contract's
+// gs_expf, exactly as the forward decided them.  gsb_selftest_work_counters counts the disagreements of
+// this function (and of the raw MUFU test) against the forward's decision on a real frame.
+__device__ __forceinline__ bool bwd_alpha_hit(const float power, const float opacity, float& G, float& alpha) {
+  G = exp_approx(power);
+  alpha = f_min(0.99f, opacity * G);
+  bool hit = !(alpha < (1.0f / 255.0f));
+  if (fabsf(alpha - (1.0f / 255.0f)) < 1e-7f)
+    hit = !(f_min(0.99f, __fmul_rn(opacity, gs_expf(power))) < (1.0f / 255.0f));
+  return hit;
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; x must be a normal number
@@ -516,10 +531,10 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       const bool actB = __float_as_int(bB.w) < kept && !(pwB > 0.0f) && !(pwB < bB.z);
       float svA = 0.0f, wvA = 0.0f, svB = 0.0f, wvB = 0.0f;
       if (actA || actB) {
-        const float GA = exp_approx(pwA), GB = exp_approx(pwB);
-        const float alphaA = f_min(0.99f, bA.y * GA), alphaB = f_min(0.99f, bB.y * GB);
-        if (actA && !(alphaA < (1.0f / 255.0f))) replay_hit(GA, alphaA, jA, svA, wvA);  // backward.py:655
-        if (actB && !(alphaB < (1.0f / 255.0f))) replay_hit(GB, alphaB, jB, svB, wvB);
+        float GA, GB, alphaA, alphaB;
+        const bool hitA = bwd_alpha_hit(pwA, bA.y, GA, alphaA), hitB = bwd_alpha_hit(pwB, bB.y, GB, alphaB);
+        if (actA && hitA) replay_hit(GA, alphaA, jA, svA, wvA);  // backward.py:655
+        if (actB && hitB) replay_hit(GB, alphaB, jB, svB, wvB);
       }
       pS[0] = svA;
       pS[kGrp * kSRow] = wvA;
@@ -535,9 +550,8 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
       float sv = 0.0f, wv = 0.0f;
       if (__float_as_int(b4.w) < kept && !(power > 0.0f) && !(power < b4.z)) {
-        const float G = exp_approx(power);
-        const float alpha = f_min(0.99f, b4.y * G);
-        if (!(alpha < (1.0f / 255.0f))) replay_hit(G, alpha, j, sv, wv);
+        float G, alpha;
+        if (bwd_alpha_hit(power, b4.y, G, alpha)) replay_hit(G, alpha, j, sv, wv);
       }
       pS[0] = sv;
       pS[kGrp * kSRow] = wv;
@@ -546,230 +560,6 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     }
     if (gslot > 0) flush_group(q - gslot, gslot);
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// Warp-autonomous replay (bwd_reduce = 3, 4).  The kernel above shares one staged batch between the
-// eight warps of a tile, which costs two CTA barriers per 256 list entries -- and the eight blocks of
-// a tile carry very different hit counts, so a fifth of all warp cycles sit behind BAR.SYNC.  Here a
-// warp owns its 4x8 block from start to end and never meets another warp:
-//   * it walks the tile's list back to front 32 entries at a time: lane l reads the culling mask and
-//     the Gaussian id of one entry (two coalesced loads, issued one chunk ahead), the lanes whose
-//     mask touches the block gather their Gaussian (issued one chunk ahead as well, held in
-//     registers while the previous chunk is replayed) and append it to a 64-slot per-warp ring;
-//   * the ring is replayed two hits at a time exactly like the staged batch above (an odd hit waits
-//     for the next chunk), the S / W tiles and the tensor-core flush are the same;
-//   * ring capacity: <= 15 replayed hits of the open MMA group (the flush reads their Gaussians) +
-//     1 waiting + 32 new = 48.
-// No __syncthreads anywhere, so the CTA is only a packing unit: WPC warps = WPC blocks of one tile.
-struct WarpRing {
-  float4 a[64];   // x, y, conic.a, conic.c
-  float4 b[64];   // conic.b, opacity, power threshold, position in the tile's list (int bits)
-  float4 c[64];   // r, g, b, gid (int bits)
-  float sw[2][kGrp][kSRow];
-};
-
-template <int WPC, int MINB>
-__global__ void __launch_bounds__(32 * WPC, MINB)
-blend_backward_warp_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
-                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
-                           const float* __restrict__ rgb, const float* __restrict__ final_T,
-                           const int* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-                           float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
-                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
-                           const unsigned* __restrict__ block_masks) {
-  constexpr unsigned full = 0xffffffffu;
-  constexpr int BPT = 8 / WPC;  // CTAs per tile
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  WarpRing& sm = reinterpret_cast<WarpRing*>(smem_raw)[threadIdx.x >> 5];
-
-  const int tile_id = blockIdx.x / BPT;
-  const int wb = (blockIdx.x % BPT) * WPC + (threadIdx.x >> 5);  // this warp's block of the tile, 0..7
-  const int tile_x = tile_id % P.grid_x, tile_y = tile_id / P.grid_x;
-  const int bx0 = tile_x * kTile + (wb & 1) * 8, by0 = tile_y * kTile + (wb >> 1) * 4;  // block origin
-  const int px = bx0 + (lane & 7);
-  const int py = by0 + (lane >> 3);
-  const gs_f2 npxy = gs_pack2(-(float)px, -(float)py);
-  const int2 range = ranges[tile_id];
-  const unsigned my_mask = gs_warp_mask(wb);
-
-  const bool inside = (px < P.W && py < P.H);
-  const size_t pix = inside ? ((size_t)py * P.W + px) : 0;
-  const float T_final = inside ? final_T[pix] : 0.0f;
-  float T = T_final;
-  const int kept = inside ? min(range.y - range.x, n_contrib[pix]) : 0;  // backward.py:619
-  const int my_max = __reduce_max_sync(full, kept);
-  if (my_max == 0) return;  // nothing was blended into this block
-  const float dp0 = inside ? dL_dpixels[3 * pix + 0] : 0.0f;
-  const float dp1 = inside ? dL_dpixels[3 * pix + 1] : 0.0f;
-  const float dp2 = inside ? dL_dpixels[3 * pix + 2] : 0.0f;
-  float gamma = T_final * gs_dot3(P.bg0, P.bg1, P.bg2, dp0, dp1, dp2);  // see blend_backward_mma_kernel
-
-  const int fg = lane >> 2, ft = lane & 3;
-  const float fr = (float)ft;
-  const float m0 = fg == 0 ? 1.0f : fg == 2 ? fr : fg == 5 ? fr * fr : 0.0f;
-  const float m1 = fg == 1 ? 1.0f : fg == 4 ? fr : 0.0f;
-  const float m2 = fg == 3 ? 1.0f : 0.0f;
-  const bool dp_row_ok = fg < 3 && (by0 + ft) < P.H;
-  const float* const dp_row = dL_dpixels + (dp_row_ok ? 3 * ((size_t)(by0 + ft) * P.W + bx0) + fg : 0);
-  const int dp_cols = dp_row_ok ? min(8, P.W - bx0) : 0;
-
-  const float ddelx_dx = 0.5f * (float)P.W;
-  const float ddely_dy = 0.5f * (float)P.H;
-  float* const tS = &sm.sw[0][0][0];
-  float* const tW = &sm.sw[1][0][0];
-  const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
-  const bool have = P.cull && block_masks != nullptr;   // the forward's masks were handed on
-  const bool need_mask = P.cull && !have;               // recompute them (same values)
-
-  int wr = 0, rd = 0;   // ring counters: appended / replayed hits (slot = counter & 63)
-  int gslot = 0;        // hits in the open MMA group
-  float* pS = tS + lane;
-
-  auto replay_hit = [&](const float G, const float alpha, const int j, float& sv, float& wv) {
-    const float4 c = sm.c[j];
-    const float inv_1ma = rcp_approx(1.0f - alpha);
-    T = T * inv_1ma;
-    wv = alpha * T;
-    const float dc = gs_dot3(c.x, c.y, c.z, dp0, dp1, dp2);
-    const float dL_dalpha = T * dc - gamma * inv_1ma;
-    gamma = fmaf(dc, wv, gamma);
-    sv = G * dL_dalpha;
-  };
-
-  // the open group's hits are the ring entries gbase .. gbase + count - 1
-  auto flush_group = [&](const int gbase, const int count) {
-    float4 m03, col;
-    float2 m45;
-    bwd_group_moments(tS, tW, lane, fg, ft, m0, m1, m2, dp_row, dp_cols, m03, m45, col);
-    if (lane < count && bwd_group_nonzero(m03, m45, col)) {
-      const int je = (gbase + lane) & 63;
-      const int gid = __float_as_int(sm.c[je].w);
-      float g[5];
-      bwd_group_gradients(sm.a[je], sm.b[je], (float)bx0, (float)by0, m03, m45, ddelx_dx, ddely_dy, g);
-      atomicAdd(dL_dcolor + 3 * (size_t)gid + 0, col.x);
-      atomicAdd(dL_dcolor + 3 * (size_t)gid + 1, col.y);
-      atomicAdd(dL_dcolor + 3 * (size_t)gid + 2, col.z);
-      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 0, g[3]);
-      atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, g[4]);
-      atomicAdd(dL_dconic + 4 * (size_t)gid + 0, g[0]);
-      atomicAdd(dL_dconic + 4 * (size_t)gid + 1, g[1]);
-      atomicAdd(dL_dconic + 4 * (size_t)gid + 3, g[2]);
-      atomicAdd(dL_dopacity + gid, m03.x);
-    }
-    __syncwarp();
-    gslot = 0;
-    pS = tS + lane;
-  };
-
-  // ---- the two-deep pipeline: (mask, id) of chunk k+2 and the Gaussians of chunk k+1 are in flight
-  // while chunk k is replayed.  Chunk with upper end `chi`: lane l looks at list position chi - 1 - l.
-  auto load_entry = [&](const int chi, unsigned& m, int& g) {
-    const int pos = chi - 1 - lane;
-    m = 0u;
-    g = 0;
-    if (pos >= 0) {
-      const int e = range.x + pos;
-      g = point_list[e];
-      m = have ? block_masks[e] : 0xffffffffu;
-    }
-  };
-  float2 gp = make_float2(0.0f, 0.0f);
-  float4 gco = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  float gc0 = 0.0f, gc1 = 0.0f, gc2 = 0.0f;
-  bool cand = false;
-  auto gather = [&](const unsigned m, const int g) {
-    // with handed-on masks only the entries that touch this block are fetched; without them every
-    // entry is (its mask is computed from what was fetched)
-    cand = need_mask ? (m != 0u) : ((m & my_mask) != 0u);
-    if (cand) {
-      gp = xy[g];
-      gco = conic_opacity[g];
-      gc0 = rgb[3 * g + 0];
-      gc1 = rgb[3 * g + 1];
-      gc2 = rgb[3 * g + 2];
-    }
-  };
-
-  int hi = my_max;
-  unsigned m_cur, m_nxt;
-  int g_cur, g_nxt;
-  load_entry(hi, m_cur, g_cur);
-  load_entry(hi - 32, m_nxt, g_nxt);
-  gather(m_cur, g_cur);
-
-  while (hi > 0) {
-    // 1. append the fetched chunk's hits to the ring, in replay order (ascending lane)
-    {
-      bool hit = cand;
-      float thr = 0.0f;
-      if (cand) {
-        thr = gs_power_threshold(gco.w);
-        if (need_mask)
-          hit = (gs_block_mask(gp.x, gp.y, gco.x, gco.y, gco.z, thr, tile_x0, tile_y0) & my_mask) != 0u;
-      }
-      const unsigned bal = __ballot_sync(full, hit);
-      if (hit) {
-        const int slot = (wr + __popc(bal & ((1u << lane) - 1u))) & 63;
-        sm.a[slot] = make_float4(gp.x, gp.y, gco.x, gco.z);
-        sm.b[slot] = make_float4(gco.y, gco.w, thr, __int_as_float(hi - 1 - lane));
-        sm.c[slot] = make_float4(gc0, gc1, gc2, __int_as_float(g_cur));
-      }
-      wr += __popc(bal);
-    }
-    // 2. advance the pipeline
-    hi -= 32;
-    m_cur = m_nxt;
-    g_cur = g_nxt;
-    cand = false;
-    if (hi > 0) {
-      gather(m_cur, g_cur);
-      load_entry(hi - 32, m_nxt, g_nxt);
-    }
-    __syncwarp();
-    // 3. replay what the ring holds, two hits per iteration; an odd hit waits for the next chunk
-    while (wr - rd >= 2) {
-      const int jA = rd & 63, jB = (rd + 1) & 63;
-      const float4 aA = sm.a[jA], bA = sm.b[jA];
-      const float4 aB = sm.a[jB], bB = sm.b[jB];
-      const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);
-      const float pwB = gs_power_packed(gs_pack2(aB.x, aB.y), npxy, gs_pack2(aB.z, aB.w), bB.x);
-      const bool actA = __float_as_int(bA.w) < kept && !(pwA > 0.0f) && !(pwA < bA.z);
-      const bool actB = __float_as_int(bB.w) < kept && !(pwB > 0.0f) && !(pwB < bB.z);
-      float svA = 0.0f, wvA = 0.0f, svB = 0.0f, wvB = 0.0f;
-      if (actA || actB) {
-        const float GA = exp_approx(pwA), GB = exp_approx(pwB);
-        const float alphaA = f_min(0.99f, bA.y * GA), alphaB = f_min(0.99f, bB.y * GB);
-        if (actA && !(alphaA < (1.0f / 255.0f))) replay_hit(GA, alphaA, jA, svA, wvA);
-        if (actB && !(alphaB < (1.0f / 255.0f))) replay_hit(GB, alphaB, jB, svB, wvB);
-      }
-      pS[0] = svA;
-      pS[kGrp * kSRow] = wvA;
-      pS[kSRow] = svB;
-      pS[kGrp * kSRow + kSRow] = wvB;
-      gslot += 2;
-      pS += 2 * kSRow;
-      rd += 2;
-      if (gslot == kGrp) flush_group(rd - kGrp, kGrp);
-    }
-  }
-  if (rd < wr) {  // the list's last hit
-    const int j = rd & 63;
-    const float4 a = sm.a[j], b4 = sm.b[j];
-    const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
-    float sv = 0.0f, wv = 0.0f;
-    if (__float_as_int(b4.w) < kept && !(power > 0.0f) && !(power < b4.z)) {
-      const float G = exp_approx(power);
-      const float alpha = f_min(0.99f, b4.y * G);
-      if (!(alpha < (1.0f / 255.0f))) replay_hit(G, alpha, j, sv, wv);
-    }
-    pS[0] = sv;
-    pS[kGrp * kSRow] = wv;
-    ++gslot;
-    ++rd;
-  }
-  if (gslot > 0) flush_group(rd - gslot, gslot);
 }
 
 // Stage-level entry point only: the packed records written out in the reference's four layouts (inside
@@ -814,10 +604,77 @@ __global__ void __launch_bounds__(256) zero_arrays_kernel(const ZeroJob job) {
   }
 }
 
+// Diagnostic: the reference's per-pixel loops (forward.py:454-501, backward.py:633-706) walked by one thread per
+// pixel with the contract's arithmetic, counting work and decisions:
+//   [0] K_fwd   (pixel, Gaussian) pairs the forward loop iterates (until the pixel breaks or its list ends)
+//   [1] pairs that blend (alpha >= 1/255, before the break)      [2] K_bwd = sum of min(list, n_contrib)
+//   [3] backward pairs whose exponent passes power <= 0 and the conservative threshold (alpha gets evaluated)
+//   [4] of those: raw MUFU test `alpha_approx < 1/255` disagrees with the forward's decision
+//   [5] of those: bwd_alpha_hit (what the backward kernel uses) disagrees      [6] of those: decided by gs_expf
+__global__ void __launch_bounds__(256)
+work_counters_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
+                     const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                     const int* __restrict__ n_contrib, unsigned long long* __restrict__ counters) {
+  const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+  unsigned long long c[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (px < P.W && py < P.H) {
+    const int2 range = ranges[blockIdx.y * P.grid_x + blockIdx.x];
+    const gs_f2 npxy = gs_pack2(-(float)px, -(float)py);
+    const int kept = min(range.y - range.x, n_contrib[(size_t)py * P.W + px]);
+    c[2] = (unsigned long long)kept;
+    float T = 1.0f;
+    for (int e = range.x; e < range.y; ++e) {
+      const int gid = point_list[e];
+      const float2 p = xy[gid];
+      const float4 co = conic_opacity[gid];
+      c[0] += 1;
+      const float power = gs_power_packed(gs_pack2(p.x, p.y), npxy, gs_pack2(co.x, co.z), co.y);
+      const bool fwd_hit = !(power > 0.0f) && !(f_min(0.99f, __fmul_rn(co.w, gs_expf(power))) < (1.0f / 255.0f));
+      if (e - range.x < kept && !(power > 0.0f) && !(power < gs_power_threshold(co.w))) {
+        c[3] += 1;
+        float G, alpha;
+        const bool hit = bwd_alpha_hit(power, co.w, G, alpha);
+        c[4] += (!(alpha < (1.0f / 255.0f))) != fwd_hit;
+        c[5] += hit != fwd_hit;
+        c[6] += fabsf(alpha - (1.0f / 255.0f)) < 1e-7f;
+      }
+      if (!fwd_hit) continue;
+      const float alpha = f_min(0.99f, __fmul_rn(co.w, gs_expf(power)));
+      const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+      if (test_T < 0.0001f) break;
+      c[1] += 1;
+      T = test_T;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    unsigned long long v = c[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counters + k, v);
+  }
+}
+
 }  // namespace
 
-extern int g_bwd_packed;
-bool gsb_blend_backward_uses_packed() { return g_bwd_packed != 0 && (g_bwd_reduce == 1 || g_bwd_reduce == 2); }
+GSB_API int gsb_selftest_work_counters(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
+                                       const int32_t* point_list, const float* points_xy, const float* conic_opacity,
+                                       const int32_t* n_contrib, uint64_t* counters7) {
+  if (!ctx) return GSB_ERR_INVALID;
+  GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0 && counters7, "gsb_selftest_work_counters: bad arguments");
+  cudaStream_t s = (cudaStream_t)s_;
+  GSB_CUDA(ctx, cudaMemsetAsync(counters7, 0, 7 * sizeof(uint64_t), s));
+  BlendParams P = make_blend_params(ctx, f);
+  dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
+  GSB_LAUNCH(ctx, work_counters_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
+             reinterpret_cast<const float2*>(points_xy), reinterpret_cast<const float4*>(conic_opacity), n_contrib,
+             reinterpret_cast<unsigned long long*>(counters7));
+  return GSB_OK;
+}
+
+bool gsb_blend_backward_uses_packed(const gsb_ctx* ctx) {
+  return ctx->opt.bwd_packed != 0 && (ctx->opt.bwd_reduce == 1 || ctx->opt.bwd_reduce == 2);
+}
 
 // The tensor-core kernel, either accumulating into the caller's four arrays (packed == nullptr; they must be
 // zero) or into packed records (which must be zero).
@@ -839,7 +696,7 @@ static int launch_backward_mma(gsb_ctx* ctx, cudaStream_t s, const BlendParams& 
              reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),               \
              reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic,  \
              dL_dopacity, dL_dcolor, masks, packed)
-  if (g_bwd_reduce == 2) {
+  if (ctx->opt.bwd_reduce == 2) {
     if (packed) GSB_BWD_MMA(4, true);
     else GSB_BWD_MMA(4, false);
   } else {
@@ -862,7 +719,7 @@ int gsb_blend_backward_packed(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, 
   job.n[0] = 12LL * n;
   const long long blocks = gsb_div_up(3LL * n, 256);  // one 16-byte store per thread
   GSB_LAUNCH(ctx, zero_arrays_kernel, (unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, s, job);
-  BlendParams P = make_blend_params(f);
+  BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
   return launch_backward_mma(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
                              dL_dpixels, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const unsigned*>(block_masks),
@@ -879,7 +736,7 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_backward: conic_opacity must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)s_;
   if (n == 0) return GSB_OK;
-  if (gsb_blend_backward_uses_packed() && gsb_aligned16(dL_dconic)) {
+  if (gsb_blend_backward_uses_packed(ctx) && gsb_aligned16(dL_dconic)) {
     // stage-level call of the default path: packed records in context scratch, then written out
     if (ctx->bwd_acc_cap < 12LL * n) {
       int rc = gsb_grow(ctx, (void**)&ctx->bwd_acc_stage, &ctx->bwd_acc_cap, 12LL * n, sizeof(float), s);
@@ -902,33 +759,13 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
     const long long blocks = gsb_div_up(n, 256);  // one 16-byte store per thread and array
     GSB_LAUNCH(ctx, zero_arrays_kernel, (unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, s, job);
   }
-  BlendParams P = make_blend_params(f);
+  BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
   const unsigned* masks = reinterpret_cast<const unsigned*>(block_masks);
-  if (g_bwd_reduce == 0) {  // A/B: warp-shuffle butterfly reduction
+  if (ctx->opt.bwd_reduce == 0) {  // A/B: warp-shuffle butterfly reduction
     GSB_LAUNCH(ctx, blend_backward_kernel, grid, 256, 0, s, P, reinterpret_cast<const int2*>(ranges), point_list,
                reinterpret_cast<const float2*>(points_xy), reinterpret_cast<const float4*>(conic_opacity), rgb, final_T,
                n_contrib, dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, masks);
-    return GSB_OK;
-  }
-  if (g_bwd_reduce >= 3) {  // warp-autonomous replay: 3 = four warps per CTA (seven CTAs per SM), 4 = eight (three)
-    const long long tiles = (long long)grid.x * grid.y;
-    if (g_bwd_reduce == 3) {
-      GSB_LAUNCH(ctx, (blend_backward_warp_kernel<4, 7>), (unsigned)(tiles * 2), 128, 4 * sizeof(WarpRing), s, P,
-                 reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
-                 reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
-                 dL_dconic, dL_dopacity, dL_dcolor, masks);
-    } else {
-      if (!ctx->smem_optin_blend_bwd_w8) {
-        GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_warp_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(8 * sizeof(WarpRing))));
-        ctx->smem_optin_blend_bwd_w8 = true;
-      }
-      GSB_LAUNCH(ctx, (blend_backward_warp_kernel<8, 3>), (unsigned)tiles, 256, 8 * sizeof(WarpRing), s, P,
-                 reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),
-                 reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D,
-                 dL_dconic, dL_dopacity, dL_dcolor, masks);
-    }
     return GSB_OK;
   }
   return launch_backward_mma(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,

@@ -9,8 +9,6 @@
 #pragma once
 #include "common.cuh"
 
-extern int g_blend_cull;
-extern int g_bwd_reduce;
 
 namespace {
 
@@ -120,7 +118,7 @@ __device__ __forceinline__ int warp_compact_hits(const int2* s_meta, int cnt, un
   return n;
 }
 
-inline BlendParams make_blend_params(const gsb_frame* f) {
+inline BlendParams make_blend_params(const gsb_ctx* ctx, const gsb_frame* f) {
   BlendParams P;
   P.W = f->width;
   P.H = f->height;
@@ -128,7 +126,7 @@ inline BlendParams make_blend_params(const gsb_frame* f) {
   P.bg0 = f->background[0];
   P.bg1 = f->background[1];
   P.bg2 = f->background[2];
-  P.cull = g_blend_cull;
+  P.cull = ctx->opt.blend_cull;
   return P;
 }
 

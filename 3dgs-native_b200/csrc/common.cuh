@@ -24,7 +24,16 @@ struct gsb_ctx {
   char err[512] = {0};
   int64_t launches = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: done once per context, not per process
-  bool smem_optin_blend_bwd = false, smem_optin_blend_bwd_w8 = false, smem_optin_radix = false, smem_optin_tilesort = false;
+  bool smem_optin_blend_bwd = false, smem_optin_radix = false, smem_optin_tilesort = false;
+  // A/B knobs of gsb_set_option (per context; results never depend on them)
+  struct Options {
+    int fuse_sort = 0;   // 1: tiles of up to 2048 entries are sorted by the forward tile kernel's own CTAs -- measured slower
+    int binning = 0;     // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
+    int blend_cull = 1;  // per-block culling masks in the tile kernels
+    int tile_sort = 0;   // 0: bitonic network for every tile (default); 1: per-tile LSD radix sort (bitonic for tiles > 4096)
+    int bwd_reduce = 2;  // 2 / 1: tensor-core pixel sums at 4 / 3 resident CTAs per SM; 0: warp-shuffle butterfly
+    int bwd_packed = 1;  // 1: the tensor-core backward accumulates into packed records with vector REDs; 0: nine scalar REDs
+  } opt;
 
   // binning scratch (grow-only): sort double buffers
   int64_t* keys_a = nullptr;
@@ -336,7 +345,7 @@ int gsb_blend_backward_packed(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, 
                               const int32_t* point_list, const float* points_xy, const float* conic_opacity,
                               const float* rgb, const float* final_T, const int32_t* n_contrib,
                               const float* dL_dpixels, float* packed, const int32_t* block_masks);
-bool gsb_blend_backward_uses_packed();
+bool gsb_blend_backward_uses_packed(const gsb_ctx* ctx);
 
 // ---- stage launchers implemented across the .cu files (host side) --------------------------
 int gsb_scan_i32(gsb_ctx* ctx, cudaStream_t s, int64_t n, const int32_t* in, int32_t* out, bool exclusive,

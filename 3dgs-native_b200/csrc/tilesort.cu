@@ -20,7 +20,6 @@
 // sort (sort.cu), which is also what the stage-level entry point gsb_sort_pairs64 runs.
 #include "tilesort.cuh"
 
-extern int g_tile_sort;
 constexpr int kMaxTileSort = 16384;
 
 namespace {
@@ -368,7 +367,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
              depths, radii, rank_index, index_is_exclusive, gx, gy, rg, ctx->vals_a, binned);
   (void)num_rendered;
   if (!point_list) return GSB_OK;
-  // Per-tile sort.  Default: the bitonic kernel.  g_tile_sort == 1 (A/B switch): the O(n) shared-memory
+  // Per-tile sort.  Default: the bitonic kernel.  tile_sort == 1 (A/B switch): the O(n) shared-memory
   // radix sort for tiles of up to 4096 entries and the bitonic kernel for longer ones (each kernel
   // skips the other's tiles).  Measured on a B200 at ~650 entries per tile the radix kernel executes
   // half the instructions but is a chain of dependent shared-memory operations and barriers (28% of
@@ -384,7 +383,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
     attr_set = true;
   }
   int bitonic_lo = 0;  // the bitonic kernel sorts tiles with more than this many entries
-  if (g_tile_sort == 1) {
+  if (ctx->opt.tile_sort == 1) {
     if (max_count <= 1024) {
       GSB_LAUNCH(ctx, tile_radix_kernel<1024>, num_tiles, 256, radix_smem(1024), s, rg, binned, point_list, 0, 1024);
     } else if (max_count <= 2048) {

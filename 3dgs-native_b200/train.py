@@ -13,9 +13,11 @@ What the reference does per iteration and what happens here instead:
 * densification_and_pruning(iteration) (1060, 351-713) -> same orchestration, same quirks
 
 Multi-GPU (not in the reference): a step's batch of views is split contiguously over the ranks,
-each rank sums the gradients of its views into one flat [59*N] buffer, ONE NCCL all-reduce sums
-the buffers, and every rank applies the identical Adam / densify step (replicas stay bit-identical
-because NCCL's result is the same on all ranks and clone/split noise is an index hash)."""
+each rank sums the gradients of its views into one flat [59*N] buffer, the buffers are summed
+(NCCL all-reduce, or the fused peer-memory exchange + Adam kernel), and every rank applies the
+identical densify step: replicas stay bit-identical because every parameter is computed once (or
+NCCL's result is the same on all ranks), the summed position gradient the candidate masks are
+computed from is published to every rank on densify steps, and clone/split noise is an index hash."""
 from __future__ import annotations
 
 import ctypes as C
@@ -49,6 +51,21 @@ def compact_sh_step(enabled: bool, num_views: int, world_size: int) -> bool:
     do not add -- and there is somebody to exchange with.  A function of global quantities only, so all
     ranks decide alike."""
     return bool(enabled) and world_size > 1 and num_views == world_size
+
+
+def shard_range(n: int, rank: int, world_size: int):
+    """The Gaussians [g0, g1) whose Adam state rank ``rank`` owns in the fused exchange modes (same rule
+    as adam_step_peers_impl, csrc/optimizer.cu: boundaries on multiples of 4 Gaussians)."""
+    g0 = (n * rank // world_size) // 4 * 4
+    g1 = n if rank == world_size - 1 else (n * (rank + 1) // world_size) // 4 * 4
+    return g0, g1
+
+
+def densify_due(config: dict, iteration: int) -> bool:
+    """train.py:385-392: the iterations on which clone / split / prune candidates are marked.  A function of
+    the iteration and the config only, so every rank of a data-parallel run decides alike."""
+    return (iteration > config["densify_from_iter"] and iteration < config["densify_until_iter"]
+            and iteration % config["densification_interval"] == 0)
 
 
 def flat_layout(n: int):
@@ -173,6 +190,7 @@ class Trainer:
         if self.config["use_lr_scheduler"]:
             self.lr_scheduler = {k: LRScheduler(sc[k], ff) for k in ("lr_pos", "lr_scale", "lr_rot", "lr_sh", "lr_opac")}
         self.fb = None
+        self._last_hw = (1, 1)
         self.losses = []
 
     # ---- state -------------------------------------------------------------------------------
@@ -311,9 +329,12 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def exchange_and_step(self, iteration, compact=None):
+    def exchange_and_step(self, iteration, compact=None, publish_position_grad=False):
         """``compact``: the SH segment of every rank's gradient buffer holds the rank-1 factors
         written by gsb_backward_compact_sh (None = whatever train_step decided for this step).
+        ``publish_position_grad`` (fused modes; nccl leaves the sum in ``self.grads`` anyway): after
+        the call every rank's ``self.grads["positions"]`` holds the gradient summed over all ranks --
+        what densification_and_pruning needs (train.py:398-433).
 
         Gradient sum over the ranks + Adam.  nccl: all_reduce then the replicated fused Adam.
         peers / multimem: ONE kernel between two cross-rank barriers -- each rank reduces its shard
@@ -337,7 +358,6 @@ class Trainer:
         p_mc = int(P.multicast_ptr) if use_mc else 0
         ev = None
         if self.exchange_events is not None:
-            import torch
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
         G.barrier(channel=0)        # every rank's backward has finished writing its gradients
@@ -349,13 +369,13 @@ class Trainer:
                 _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
                 lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
                 self.config["adam_epsilon"], iteration, _lib.ptr(self.sh_local), self.sh_local.numel(),
-                self.config["sh_degree"]))
+                self.config["sh_degree"], int(bool(publish_position_grad))))
         else:
             self.ctx.check(_lib.lib().gsb_adam_step_peers(
                 self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, g_mc, p_mc,
                 _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
                 lr["lr_opac"], lr["lr_sh"], self.config["adam_beta1"], self.config["adam_beta2"],
-                self.config["adam_epsilon"], iteration))
+                self.config["adam_epsilon"], iteration, int(bool(publish_position_grad))))
         if ev:
             ev[2].record()
         P.barrier(channel=1)        # every rank's parameter shard has landed everywhere
@@ -376,38 +396,54 @@ class Trainer:
             ci = cam_indices[b]
             tgt = targets[b] if targets is not None else self.targets[ci]
             fb = self.accumulate_view(ci, tgt, first=(j == 0))
+        self._last_hw = (fb.H, fb.W)
+        loss_sum = fb.loss_sum           # densify may drop the frame buffers; the scalar tensor stays alive
+        # a function of the iteration and the config only: every rank decides alike
+        publish = bool(densify) and self.densify_due(iteration)
         if self.exchange_events is not None:     # bench.py: device time of the exchange + Adam part
-            import torch
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.exchange_and_step(iteration)
+            self.exchange_and_step(iteration, publish_position_grad=publish)
             e1.record()
             self.exchange_events.append((e0, e1))
         else:
-            self.exchange_and_step(iteration)
+            self.exchange_and_step(iteration, publish_position_grad=publish)
         if densify:
             self.densification_and_pruning(iteration)
-        return fb.loss_sum
+        return loss_sum
 
     # ---- densify / prune, train.py:351-713 ------------------------------------------------------
+    def densify_due(self, iteration) -> bool:
+        return densify_due(self.config, iteration)
+
     def _alloc_like(self, n):
-        return self._new_flat(n)                       # wp.zeros outputs of train.py:441-447 etc.
+        """The wp.zeros outputs of train.py:441-447 etc.  Intermediate Gaussian sets of one densify call live in
+        plain device memory; only the set that survives the call is moved into symmetric memory (_replace):
+        one rendezvous per densify event instead of one per clone / split / compact."""
+        return FlatGaussians(n, self.device)
 
     def _replace(self, new: FlatGaussians):
+        """train.py:474-476 and its siblings: new parameter set, gradients and Adam moments reset to zeros."""
+        if self.exchange in ("peers", "multimem") and new.symm is None:
+            sym = self._new_flat(new.n)          # collective: every rank arrives here with the same count
+            sym.flat.copy_(new.flat)
+            new = sym
         self.params, self.num_points = new, new.n
-        self._alloc_state()                            # train.py:474-476: grads, m, v all reset to zeros
+        self._alloc_state()
 
     def densification_and_pruning(self, iteration):
+        """train.py:351-713.  Multi-GPU: every rank runs this on identical inputs (parameters are replicas,
+        ``self.grads["positions"]`` holds the all-rank sum: NCCL's result, or published by the fused exchange
+        kernel), so masks, counts and the new parameter sets are identical without any further exchange."""
         cfg = self.config
         log = {"cloned": 0, "split": 0, "split_removed": 0, "pruned": 0, "opacity_reset": False}
         i32 = torch.int32
-        if (iteration > cfg["densify_from_iter"] and iteration < cfg["densify_until_iter"]
-                and iteration % cfg["densification_interval"] == 0):
+        if self.densify_due(iteration):
             n = self.num_points
             avg_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
             optimizer.compute_grad_norms(self.grads["positions"], avg_grads, n)
             gt, pd, ext = cfg["densify_grad_threshold"], cfg["percent_dense"], self.scene_extent
-            P = self.params
+            P = cur = self.params                # `cur`: the Gaussian set as the reference's self.params sees it
             clone_mask = torch.zeros(n, dtype=i32, device=self.device)
             optimizer.mark_clone_candidates(avg_grads, P["scales"], gt, ext, pd, n, clone_mask)
             clone_prefix = torch.zeros_like(clone_mask)
@@ -417,9 +453,9 @@ class Trainer:
                 optimizer.clone_gaussians(clone_mask, clone_prefix, P["positions"], P["scales"], P["rotations"],
                                           P["opacities"], P["shs"], 0.01, n, out["positions"], out["scales"],
                                           out["rotations"], out["opacities"], out["shs"])
-                self._replace(out)
+                cur = out
                 log["cloned"] = total_to_clone
-            n, P = self.num_points, self.params
+            n, P = cur.n, cur
             split_mask = torch.zeros(n, dtype=i32, device=self.device)
             # quirk G4: avg_grads still has the pre-clone length
             optimizer.mark_split_candidates(avg_grads, P["scales"], gt, ext, pd, n, split_mask)
@@ -432,9 +468,8 @@ class Trainer:
                 optimizer.split_gaussians(split_mask, split_prefix, P["positions"], P["scales"], P["rotations"],
                                           P["opacities"], P["shs"], n_split, 0.8, N0, out["positions"], out["scales"],
                                           out["rotations"], out["opacities"], out["shs"])
-                self._replace(out)
+                P = cur = out
                 log["split"] = total_to_split
-                P = self.params
                 valid = torch.zeros(new_n, dtype=i32, device=self.device)
                 optimizer.split_valid_mask(split_mask, valid, N0, new_n)
                 prefix = torch.zeros_like(valid)
@@ -445,8 +480,8 @@ class Trainer:
                                                 P["opacities"], P["shs"], out["positions"], out["scales"],
                                                 out["rotations"], out["opacities"], out["shs"])
                     log["split_removed"] = new_n - valid_count
-                    self._replace(out)
-            n, P = self.num_points, self.params
+                    cur = out
+            n, P = cur.n, cur
             valid = torch.zeros(n, dtype=i32, device=self.device)
             optimizer.prune_gaussians(P["opacities"], cfg["cull_opacity_threshold"], n, valid)
             prefix = torch.zeros_like(valid)
@@ -459,8 +494,10 @@ class Trainer:
                 optimizer.compact_gaussians(valid, prefix, P["positions"], P["scales"], P["rotations"], P["opacities"],
                                             P["shs"], out["positions"], out["scales"], out["rotations"],
                                             out["opacities"], out["shs"])
-                self._replace(out)
+                cur = out
                 log["pruned"] = prune_count
+            if cur is not self.params:
+                self._replace(cur)               # gradients and Adam moments restart from zeros (train.py:474-476)
         background_is_white = all(c == 1.0 for c in cfg["background_color"])
         if (iteration % cfg["opacity_reset_interval"] == 0
                 or (background_is_white and iteration == cfg["densify_from_iter"])):   # quirk G6: iteration 0 too
@@ -469,44 +506,73 @@ class Trainer:
         return log
 
     # ---- checkpoints (train.py:796-849 saves the PLY only; here the run can also be resumed) ------
+    def gathered_moments(self):
+        """The full Adam moments as (m, v) flat CUDA tensors.  In the fused exchange modes a rank only ever
+        updates the moments of its own shard of Gaussians (shard_range): the shards are put together with one
+        all-reduce of buffers that are zero outside the owner's shard.  Collective when world_size > 1."""
+        if self.exchange not in ("peers", "multimem"):
+            return self.adam_m.flat, self.adam_v.flat
+        import torch.distributed as dist
+        g0, g1 = shard_range(self.num_points, self.rank, self.world_size)
+        offs, _total = flat_layout(self.num_points)
+        out = []
+        for src in (self.adam_m.flat, self.adam_v.flat):
+            t = torch.zeros_like(src)
+            for k in KEYS:
+                a, b = offs[k] + g0 * WIDTH[k], offs[k] + g1 * WIDTH[k]
+                t[a:b] = src[a:b]
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)   # x + 0 + ... + 0: exact
+            out.append(t)
+        return out[0], out[1]
+
     def save_checkpoint(self, directory, iteration):
         """point_cloud/iteration_N/point_cloud.ply in the reference's layout (save_ply) + loss.txt,
-        plus state.npz (Adam moments, iteration) which the reference does not have."""
+        plus state.npz (Adam moments, iteration) which the reference does not have.  Collective when
+        world_size > 1 (the moment shards are gathered); rank 0 alone writes the files."""
         import os
         from .utils.point_cloud_utils import save_ply
         ckpt = os.path.join(str(directory), "point_cloud", f"iteration_{iteration}")
-        os.makedirs(ckpt, exist_ok=True)
-        save_ply(self.params.as_dict(), os.path.join(ckpt, "point_cloud.ply"), self.num_points)
-        with open(os.path.join(str(directory), "loss.txt"), "w") as f:
-            for row in self.losses:
-                f.write(f"{row[1] if isinstance(row, tuple) else row}\n")
-        np.savez(os.path.join(ckpt, "state.npz"), iteration=iteration, num_points=self.num_points,
-                 adam_m=self.adam_m.flat.cpu().numpy(), adam_v=self.adam_v.flat.cpu().numpy())
+        m, v = self.gathered_moments()
+        if self.rank == 0:
+            os.makedirs(ckpt, exist_ok=True)
+            save_ply(self.params.as_dict(), os.path.join(ckpt, "point_cloud.ply"), self.num_points)
+            with open(os.path.join(str(directory), "loss.txt"), "w") as f:
+                for row in self.losses:
+                    f.write(f"{row[1] if isinstance(row, tuple) else row}\n")
+            np.savez(os.path.join(ckpt, "state.npz"), iteration=iteration, num_points=self.num_points,
+                     adam_m=m.cpu().numpy(), adam_v=v.cpu().numpy())
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.pg)          # the files exist when any rank returns
         return ckpt
 
     def load_checkpoint(self, ckpt_dir):
-        """Restores parameters (bit-exact: the PLY stores raw float32) and the Adam state; returns the
-        iteration to continue from."""
+        """Restores parameters (bit-exact: the PLY stores raw float32) and the Adam state (every rank loads
+        the full moments; in the fused exchange modes it goes on using its own shard of them); returns the
+        iteration to continue from -- pass it to ``train(start_iteration=...)``."""
         import os
         from .utils.point_cloud_utils import load_ply
         params = load_ply(os.path.join(str(ckpt_dir), "point_cloud.ply"))
         st = np.load(os.path.join(str(ckpt_dir), "state.npz"))
-        self._replace(self._new_flat(int(st["num_points"])).load(params))
+        self._replace(FlatGaussians(int(st["num_points"]), self.device).load(params))
         self.adam_m.flat.copy_(torch.from_numpy(st["adam_m"]))
         self.adam_v.flat.copy_(torch.from_numpy(st["adam_v"]))
         return int(st["iteration"]) + 1
 
     # ---- the reference's loop --------------------------------------------------------------------
-    def train(self, num_iterations=None, batch_size=1, seed=42, log_every=0):
+    def train(self, num_iterations=None, batch_size=1, seed=42, log_every=0, start_iteration=0):
         """train.py:920-1066 with a seeded camera sampler; losses are read back every ``log_every``
-        steps only (the reference blocks on the loss every iteration)."""
+        steps only (the reference blocks on the loss every iteration).  ``start_iteration``: continue a
+        run restored by load_checkpoint -- the sampler is advanced past the iterations already done, so
+        the camera sequence is the one an uninterrupted run would have seen."""
         T = num_iterations or self.config["num_iterations"]
         rng = np.random.default_rng(seed)
         for it in range(T):
             cams = [int(rng.integers(0, len(self.cameras))) for _ in range(batch_size)]
+            if it < start_iteration:
+                continue
             loss_sum = self.train_step(it, cams)
             if log_every and it % log_every == 0:
-                fb = self.fb
-                H, W = (fb.H, fb.W) if fb is not None else (1, 1)
+                H, W = self._last_hw
                 self.losses.append((it, float(loss_sum.item()) / (3 * H * W), self.num_points))
         return self.losses

@@ -68,7 +68,7 @@ const char* gsb_last_error_string(gsb_ctx* ctx);
 int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered);
 /* number of kernel launches issued through this context so far (bench.py gpu_launches) */
 int64_t gsb_launch_count(gsb_ctx* ctx);
-/* tuning / A-B knobs outside the reference surface (process-wide; results never depend on them):
+/* tuning / A-B knobs outside the reference surface (per context; results never depend on them):
  *   "blend_cull" = 1 (default) / 0: per-block culling masks in the tile kernels
  *   "bwd_reduce" = 2 (default) / 1: the backward tile kernel sums the per-pixel terms over a warp's
  *                  pixel block with TF32 tensor-core products (4 / 3 resident CTAs per SM);
@@ -225,12 +225,16 @@ int gsb_flat_layout(int32_t n, int64_t* offsets5, int64_t* total);
  * the same buffers or 0.  The kernel sums the gradients of this rank's shard of Gaussians over all
  * ranks (multimem.ld_reduce through the NVSwitch, or one NVLink load per peer), applies
  * adam_update (optimizer.py:6-139) to the shard of m_flat / v_flat, and stores the new parameters
- * into every rank's buffer.  The caller orders it between two cross-rank barriers. */
+ * into every rank's buffer.  The caller orders it between two cross-rank barriers.
+ * publish_position_grad != 0 (densify steps): the SUMMED position gradient of the shard is also stored
+ * back into every rank's gradient buffer, so that after the closing barrier every rank's positions
+ * segment holds the all-reduced gradient that compute_grad_norms / mark_*_candidates (train.py:398-433)
+ * read -- every rank then marks, clones, splits and prunes the same Gaussians. */
 int gsb_adam_step_peers(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, int32_t rank,
                         const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host, uint64_t grad_multicast,
                         uint64_t param_multicast, float* m_flat, float* v_flat, float lr_pos, float lr_scale,
                         float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
-                        int32_t iteration);
+                        int32_t iteration, int32_t publish_position_grad);
 
 /* gsb_adam_step_peers for gradient buffers written by gsb_backward_compact_sh: the SH segment of every
  * rank's flat gradient buffer starts with that rank's float[N][8] factors.  The owner of a Gaussian
@@ -243,7 +247,19 @@ int gsb_adam_step_peers_compact(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t w
                                 const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host,
                                 uint64_t param_multicast, float* m_flat, float* v_flat, float lr_pos, float lr_scale,
                                 float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
-                                int32_t iteration, float* sh_local, int64_t sh_local_floats, int32_t degree);
+                                int32_t iteration, float* sh_local, int64_t sh_local_floats, int32_t degree,
+                                int32_t publish_position_grad);
+
+/* Diagnostic (no reference counterpart): the reference's per-pixel loops (forward.py:454-501, backward.py:633-706)
+ * walked by one thread per pixel with the arithmetic contract, counting work and decisions on a rendered frame.
+ * counters7 (device, 7 x uint64, zeroed by the call):
+ *   [0] K_fwd: (pixel, Gaussian) pairs the forward loop iterates   [1] pairs that blend   [2] K_bwd: sum of
+ *   min(list length, n_contrib)   [3] backward pairs whose alpha gets evaluated   [4] of those, pairs on which the raw
+ *   MUFU test alpha < 1/255 disagrees with the forward's decision   [5] pairs on which the backward kernel's decision
+ *   (MUFU, re-decided with the contract's exp inside a band around 1/255) disagrees: must be 0   [6] pairs in the band. */
+int gsb_selftest_work_counters(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, const int32_t* ranges,
+                               const int32_t* point_list, const float* points_xy, const float* conic_opacity,
+                               const int32_t* n_contrib, uint64_t* counters7);
 
 /* replaces zero_gradients (train.py:94-115) -- and any other "fill float" need */
 int gsb_fill_f32(gsb_ctx* ctx, gsb_stream s, float* dst, int64_t count, float value);

@@ -341,7 +341,43 @@ def case_misc():
     print("ref_misc written")
 
 
+def case_cameras():
+    """utils/camera_utils.py:8-91 load_camera on all 100 Lego train poses (800x800, the headline size) and on a
+    non-square frame, plus NeRFGaussianSplattingTrainer.calculate_scene_extent (train.py:233-257) called unbound on a
+    stand-in object; and the zero_gradients kernel (train.py:94-115) run on non-zero arrays."""
+    tr = json.load(open(os.path.join(REF, "data/lego/transforms_train.json")))
+    out = {}
+    for tag, (W, H) in (("sq", (800, 800)), ("hd", (1920, 1080))):
+        focal = 0.5 * W / np.tan(0.5 * tr["camera_angle_x"])        # train.py:297
+        cams = [load_camera({"camera_id": i, "camera_to_world": f["transform_matrix"], "width": W, "height": H,
+                             "focal": focal}) for i, f in enumerate(tr["frames"])]
+        for key in ("world_to_camera", "full_proj_matrix", "camera_center", "view_matrix", "proj_matrix", "R", "T"):
+            out[f"{tag}_{key}"] = np.stack([np.asarray(c[key]) for c in cams])
+        for key in ("tan_fovx", "tan_fovy", "fx", "fy", "cx", "cy"):
+            out[f"{tag}_{key}"] = np.array([c[key] for c in cams], dtype=np.float64)
+        holder = types.SimpleNamespace(cameras=cams, config={})
+        out[f"{tag}_scene_extent"] = np.float64(ref_train.NeRFGaussianSplattingTrainer.calculate_scene_extent(holder))
+    rng = np.random.default_rng(12)
+    n = 37
+    dt = {"positions": wp.vec3, "scales": wp.vec3, "rotations": wp.vec4, "opacities": float, "shs": wp.vec3}
+    width = {"positions": 3, "scales": 3, "rotations": 4, "opacities": 1, "shs": 3}
+    arrs = {}
+    for k in dt:
+        rows = (n + 3) * (16 if k == "shs" else 1)      # three Gaussians beyond num_points must stay untouched
+        a = rng.normal(size=(rows, width[k]) if width[k] > 1 else (rows,)).astype(np.float32)
+        out["zg_in_" + k] = a
+        arrs[k] = wp.array(a, dtype=dt[k])
+    wp.launch(ref_train.zero_gradients, dim=n + 3, inputs=[arrs["positions"], arrs["scales"], arrs["rotations"],
+                                                           arrs["opacities"], arrs["shs"], n])
+    for k in dt:
+        out["zg_out_" + k] = npy(arrs[k])
+    out["zg_n"] = np.int64(n)
+    np.savez_compressed(os.path.join(HERE, "ref_cameras.npz"), **out)
+    print("ref_cameras written", out["sq_scene_extent"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lego_small", "lego_deg1", "lego_bg", "example_scene", "adam", "densify", "loss", "loss2", "misc"]
+    which = sys.argv[1:] or ["lego_small", "lego_deg1", "lego_bg", "example_scene", "adam", "densify", "loss", "loss2", "misc",
+                             "cameras"]
     for w in which:
         globals()["case_" + w]()

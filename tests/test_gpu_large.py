@@ -4,8 +4,12 @@
   against the CPU oracle (run on all host cores for the forward; the backward oracle runs
   multi-threaded too -- its float atomics make the summation order vary, which the 1e-3 tolerance
   absorbs).
-* config 5 (6M Gaussians, 3840x2160, forward only): the oracle would need minutes, so the result is
-  checked through size-independent properties of the domain (partition, sortedness, conservation).
+* config 5 (6M Gaussians, 3840x2160, forward only): the same comparison with the oracle (about ten seconds on the
+  box's cores), plus size-independent properties of the domain (partition, sortedness, conservation).
+* gradients: norm-wise rel 1e-3 per tensor AND element-wise |d| <= 1e-3 |ref| + 1e-4 rms(ref) for EVERY element
+  (measured by tools/parity_probe.py on a B200: norm-wise 0.6e-6 .. 1.9e-6, no element beyond the bound at C2 and C3,
+  at most two beyond a ten times smaller floor); the backward's alpha >= 1/255 decisions are counted against the
+  forward's (measured: the raw MUFU test flips 1 of 42M pairs at C2, 2 of 144M at C3; the kernel's re-decision: 0).
 """
 import numpy as np
 import pytest
@@ -15,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 INT_KEYS = ["radii", "point_offsets", "point_list", "ranges", "n_contrib"]
 GRAD_KEYS = ["dL_dmean3D", "dL_dcolor", "dL_dshs", "dL_dopacity", "dL_dscale", "dL_drot", "dL_dmean2D", "dL_dconic"]
+ELEMENTWISE_MAX_VIOLATIONS = 0
 
 
 @pytest.fixture(scope="module")
@@ -35,7 +40,7 @@ def test_full_size_forward_backward_vs_oracle(gs, oracle, cfg):
     img, depth, buf = gs.forward.render_gaussians(**kw)
     oracle.set_threads(oracle.max_threads())
     try:
-        o_img, o_depth, ob = oracle.render_gaussians(**kw)
+        o_img, o_depth, ob = oracle.render_gaussians(**kw, return_extra=True)
         for k in INT_KEYS:
             a, b = buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]
             assert np.array_equal(a, b), f"{cfg} {k}: {np.count_nonzero(a != b)} of {b.size} differ"
@@ -45,7 +50,7 @@ def test_full_size_forward_backward_vs_oracle(gs, oracle, cfg):
             assert int((ob["radii"] > 0).sum()) == 283155 and ob["point_list"].size == 1614352
         dpix = oracle.compute_image_gradients(o_img, target, lambda_dssim=0)
         g = gs.backward.backward(**gs.scene.backward_kwargs(params, cam, buf, dpix))
-        og = oracle.backward(**gs.scene.backward_kwargs(params, cam, ob, dpix))
+        og = oracle.backward(**gs.scene.backward_kwargs(params, cam, ob, dpix), return_extra=True)
     finally:
         oracle.set_threads(1)
     for k in GRAD_KEYS:
@@ -53,7 +58,59 @@ def test_full_size_forward_backward_vs_oracle(gs, oracle, cfg):
         b = og[k].astype(np.float64)
         rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
         assert rel <= 1e-3, (cfg, k, rel)
+        # element-wise: north_star's "rel 1e-3 on gradients" per ELEMENT, with an absolute floor of 1e-4 of the
+        # tensor's rms (an element that is a cancelling sum of terms far larger than itself cannot be held to a
+        # relative bound).  Allowed violations: ELEMENTWISE_MAX_VIOLATIONS per tensor (measured: tools/parity_probe.py)
+        rms = np.sqrt(np.mean(b * b))
+        bad = int((np.abs(a - b) > 1e-3 * np.abs(b) + 1e-4 * rms).sum())
+        assert bad <= ELEMENTWISE_MAX_VIOLATIONS, (cfg, k, bad, b.size)
     assert not g["dL_dcov3D"].any()
+    # the backward's one decision per pair (alpha >= 1/255) against the forward's, counted on this frame
+    c = work_counters(gs, cam, buf, w, h)
+    # work counters of SURVEY 8d: the pairs the reference's loops iterate, as the oracle counted them
+    assert c["K_fwd"] == ob["_pairs_fwd"] and c["K_bwd"] == og["_pairs_bwd"] == int(ob["n_contrib"].astype(np.int64).sum())
+    assert c["K_fwd"] >= c["K_bwd"] > c["pairs_blended"] > 0
+    assert c["bwd_decision_mismatch"] == 0, c
+    assert c["mufu_raw_mismatch"] <= 1e-5 * c["bwd_pairs_evaluated"], c      # what the band re-decision removes
+
+
+def work_counters(gs, cam, buf, w, h):
+    import ctypes as C
+    from gsb200 import _lib
+    ctx = _lib.context()
+    frame = _lib.make_frame(cam["world_to_camera"], cam["full_proj_matrix"], cam["camera_center"], cam["tan_fovx"],
+                            cam["tan_fovy"], w, h, (0.0, 0.0, 0.0), 3, True, 1.0)
+    out = torch.zeros(7, dtype=torch.int64, device="cuda")
+    p = _lib.ptr
+    ctx.check(_lib.lib().gsb_selftest_work_counters(ctx.h, _lib.stream_ptr(ctx.device_index), C.byref(frame),
+                                                    p(buf["ranges"]), p(buf["point_list"]), p(buf["points_xy_image"]),
+                                                    p(buf["conic_opacity"]), p(buf["n_contrib"]), p(out)))
+    torch.cuda.synchronize()
+    names = ("K_fwd", "pairs_blended", "K_bwd", "bwd_pairs_evaluated", "mufu_raw_mismatch", "bwd_decision_mismatch",
+             "pairs_in_exact_band")
+    return dict(zip(names, [int(x) for x in out.cpu()]))
+
+
+def test_config5_forward_vs_oracle(gs, oracle):
+    """6M Gaussians at 3840x2160 against the oracle (forward.py:384-515, 517-586): radii, offsets, the whole sorted
+    point_list (68M entries), tile ranges and n_contrib bit-exact; image and inverse depth within 1e-4."""
+    n, w, h, smin, smax = gs.scene.CONFIGS["C5"]
+    params, cam, _ = gs.scene.synthetic_scene(n, w, h, smin, smax, with_target=False)
+    kw = gs.scene.render_kwargs(params, cam)
+    img, depth, buf = gs.forward.render_gaussians(**kw)
+    torch.cuda.synchronize()
+    oracle.set_threads(oracle.max_threads())
+    try:
+        o_img, o_depth, ob = oracle.render_gaussians(**kw)
+    finally:
+        oracle.set_threads(1)
+    for k in INT_KEYS:
+        a, b = buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]
+        assert np.array_equal(a, b), f"C5 {k}: {np.count_nonzero(a != b)} of {b.size} differ"
+    assert ob["point_list"].size > 50_000_000
+    assert np.abs(img.cpu().numpy() - o_img).max() <= 1e-4
+    assert np.abs(depth.cpu().numpy() - o_depth).max() <= 1e-4 * max(1.0, float(np.abs(o_depth).max()))
+    assert np.array_equal(buf["final_Ts"].cpu().numpy(), ob["final_Ts"])       # T follows the exact contract
 
 
 def test_config5_forward_properties(gs):

@@ -299,10 +299,10 @@ def test_compact_sh_gradient_expands_to_the_same_bits(gs, degree):
             scratch = torch.empty(48 * (n + 8), dtype=torch.float32, device=dev)
             ctx.check(_lib.lib().gsb_adam_step_peers_compact(
                 ctx.h, stream, n, 1, 0, gp, pp, 0, p(M.flat), p(V.flat), *lrs, 0.9, 0.999, 1e-8, 5, p(scratch),
-                scratch.numel(), degree))
+                scratch.numel(), degree, 0))
         else:
             ctx.check(_lib.lib().gsb_adam_step_peers(
-                ctx.h, stream, n, 1, 0, gp, pp, 0, 0, p(M.flat), p(V.flat), *lrs, 0.9, 0.999, 1e-8, 5))
+                ctx.h, stream, n, 1, 0, gp, pp, 0, 0, p(M.flat), p(V.flat), *lrs, 0.9, 0.999, 1e-8, 5, 0))
         torch.cuda.synchronize()
         runs[compact] = (P.flat.clone(), M.flat.clone(), V.flat.clone(), G)
     assert torch.equal(runs[False][3]["shs"].reshape(-1), g["dL_dshs"].reshape(-1))   # the stage call = the operator
@@ -315,3 +315,94 @@ def test_compact_sh_gradient_expands_to_the_same_bits(gs, degree):
     norm = fac[:, 3:6].norm(dim=1)
     live = norm > 0
     assert bool(((norm[live] - 1).abs() < 1e-5).all()) and bool((fac[:, 6:] == 0).all())
+
+
+def test_init_gaussian_params_matches_reference_source(gs, golden_dir, oracle):
+    """the CUDA init kernel against what the reference's init_gaussian_params (train.py:36-92)
+    produced under the Warp shim (ref_misc.npz) -- incl. the wp.randf positions -- and against the oracle at a
+    size that is not a multiple of the CTA."""
+    g = np.load(os.path.join(golden_dir, "ref_misc.npz"))
+    dev = torch.device("cuda")
+    for n, want in ((32, {k: g["init_" + k] for k in KEYS}), (70001, oracle.init_gaussian_params(70001, 0.1))):
+        P = gs.train.FlatGaussians(n, dev, fill=None)
+        P.flat.fill_(float("nan"))                  # the kernel must write every element
+        gs.optimizer.init_gaussian_params(P["positions"], P["scales"], P["rotations"], P["opacities"], P["shs"], n, 0.1)
+        for k in KEYS:
+            got = P[k].cpu().numpy()
+            assert np.array_equal(got, np.asarray(want[k]).reshape(got.shape)), (n, k)
+
+
+def test_zero_gradients_matches_reference_source(gs, golden_dir):
+    """zero_gradients (train.py:94-115) run by the reference's own kernel under the shim on non-zero
+    arrays that are three Gaussians longer than num_points: the first num_points entries become zero, the tail
+    keeps its values."""
+    g = np.load(os.path.join(golden_dir, "ref_cameras.npz"))
+    n = int(g["zg_n"])
+    arrs = {k: _cuda(g["zg_in_" + k]) for k in KEYS}
+    gs.optimizer.zero_gradients(arrs["positions"], arrs["scales"], arrs["rotations"], arrs["opacities"], arrs["shs"], n)
+    for k in KEYS:
+        want = g["zg_out_" + k]
+        assert np.array_equal(arrs[k].cpu().numpy(), want), k
+        assert not want[: n * (16 if k == "shs" else 1)].any() and want[n * (16 if k == "shs" else 1):].all()
+
+
+def test_step_loop_with_densify_vs_oracle(gs, oracle):
+    """eight iterations of the reference loop (train.py:926-1064) crossing two
+    densify events (clone + split + prune at iterations 4 and 8), on the GPU and in the oracle, for the same
+    camera sequence.  The Gaussian count after every iteration must be the oracle's -- exactly, unless a
+    candidate sits so close to a threshold that the 1e-3 gradient tolerance can flip it; the oracle counts those
+    (the first event is constructed to have none: the gradient threshold lies in a 2% gap of the norms)."""
+    from gsb200.utils.camera_utils import load_nerf_cameras
+    n, w, h = 3000, 96, 64
+    params, _cam0, _ = gs.scene.synthetic_scene(n, w, h, 0.02, 0.12, seed=11)
+    cams = load_nerf_cameras(w, h)[:6]
+    rng = np.random.default_rng(1)
+    targets = [rng.uniform(0, 1, (h, w, 3)).astype(np.float32) for _ in cams]
+    cfg = {"densify_from_iter": 0, "densification_interval": 4, "densify_grad_threshold": 0.00045, "percent_dense": 0.015,
+           "cull_opacity_threshold": 0.1, "min_valid_points": 100}
+    T = gs.train.Trainer(cams, targets=targets, params=params,
+                         config={"num_iterations": 7000, "use_lr_scheduler": False, **cfg})
+    st = {"params": {k: params[k].copy() for k in KEYS}, "grads": oracle.zeros_like_params(n),
+          "adam_m": oracle.zeros_like_params(n), "adam_v": oracle.zeros_like_params(n), "num_points": n,
+          "scene_extent": T.scene_extent}
+    seq = [0, 3, 5, 1, 2, 4, 0, 3]
+    oracle.set_threads(oracle.max_threads())
+    slack, events = 0, 0
+    try:
+        for it in range(1, 9):
+            ci = seq[it - 1]
+            loss_sum = T.train_step(it, [ci], densify=True)
+            P, m = st["params"], st["num_points"]
+            img, _, buf = oracle.render_gaussians(**gs.scene.render_kwargs(P, cams[ci]))
+            dpix = oracle.compute_image_gradients(img, targets[ci], lambda_dssim=0)
+            og = oracle.backward(**gs.scene.backward_kwargs(P, cams[ci], buf, dpix))
+            st["grads"] = {"positions": og["dL_dmean3D"], "scales": og["dL_dscale"], "rotations": og["dL_drot"],
+                           "opacities": og["dL_dopacity"], "shs": og["dL_dshs"]}
+            oracle.adam_update(st["grads"], P, st["adam_m"], st["adam_v"], m, 1e-2, 5e-3, 5e-3, 5e-3, 2e-3, 0.9, 0.999,
+                               1e-8, it)
+            assert float(loss_sum.item()) / (3 * h * w) == pytest.approx(oracle.l1_loss(img, targets[ci]), rel=5e-3), it
+            if T.densify_due(it):
+                # candidates the tolerance could flip: gradient norm within 0.5% of the threshold, largest scale
+                # within 0.1% of percent_dense * extent, opacity within 0.1% of the cull threshold
+                nr = np.linalg.norm(st["grads"]["positions"], axis=1)
+                gt, sthr = cfg["densify_grad_threshold"], cfg["percent_dense"] * T.scene_extent
+                near = int((np.abs(nr - gt) < 5e-3 * gt).sum())
+                near += int((np.abs(P["scales"].max(axis=1) - sthr) < 1e-3 * sthr).sum())
+                near += int((np.abs(P["opacities"] - 0.1) < 1e-4).sum())
+                if events == 0:
+                    assert near <= 4, "the first event is meant to have (almost) no borderline candidates"
+                slack += 3 * near          # a flipped split adds two Gaussians and removes one
+                events += 1
+            log = oracle.densification_and_pruning(st, it, cfg)
+            if T.densify_due(it):
+                assert log["cloned"] > 0 and log["split"] > 0 and log["pruned"] > 0, log
+            assert abs(T.num_points - st["num_points"]) <= slack, (it, T.num_points, st["num_points"], slack)
+            if T.num_points == st["num_points"] and it == 4:
+                # same masks => the same Gaussians in the same order: parameters agree like in the plain loop
+                for k in KEYS:
+                    a, b = T.params[k].cpu().numpy().astype(np.float64), st["params"][k].astype(np.float64)
+                    b = b.reshape(a.shape)
+                    assert np.linalg.norm(a - b) <= 5e-3 * np.linalg.norm(b), (k, it)
+    finally:
+        oracle.set_threads(1)
+    assert events == 2 and T.num_points != n

@@ -16,3 +16,27 @@ def test_make_frame_keeps_row_major_matrices():
     assert list(f.proj) == p.reshape(-1).tolist()
     assert (f.width, f.height, f.degree, f.clamped) == (80, 60, 2, 0)
     assert abs(f.scale_modifier - 1.5) < 1e-7 and abs(f.tan_fovy - 0.4) < 1e-7
+
+
+@pytest.mark.parametrize("tag,size", [("sq", (800, 800)), ("hd", (1920, 1080))])
+def test_load_camera_matches_reference_source(golden_dir, tag, size):
+    """the camera struct.  tests/golden/ref_cameras.npz holds what the reference's own
+    utils/camera_utils.py:8-91 load_camera returned (run unmodified by make_golden.py case_cameras) for all 100
+    Lego train poses; ours must return the same bits for every matrix the rasterizer consumes -- world_to_camera
+    (translation in the last row), full_proj_matrix, camera_center, tan_fov -- and for the malformed view_matrix
+    render.py:112 uses; scene_extent restates train.py:233-257."""
+    import os
+    import gsb200  # noqa: F401
+    from gsb200.utils.camera_utils import load_nerf_cameras, scene_extent
+    g = np.load(os.path.join(golden_dir, "ref_cameras.npz"))
+    W, H = size
+    cams = load_nerf_cameras(W, H)
+    assert len(cams) == g[f"{tag}_world_to_camera"].shape[0] == 100
+    for key in ("world_to_camera", "full_proj_matrix", "camera_center", "view_matrix", "proj_matrix", "R", "T"):
+        ours = np.stack([np.asarray(c[key]) for c in cams])
+        want = g[f"{tag}_{key}"]
+        assert ours.dtype == want.dtype and np.array_equal(ours, want), key
+    for key in ("tan_fovx", "tan_fovy", "fx", "fy", "cx", "cy"):
+        assert np.array_equal(np.array([c[key] for c in cams], dtype=np.float64), g[f"{tag}_{key}"]), key
+    assert scene_extent(cams, 1.0) == float(g[f"{tag}_scene_extent"])
+    assert all(c["width"] == W and c["height"] == H for c in cams)

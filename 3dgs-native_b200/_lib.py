@@ -14,7 +14,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libgsb200.so")
+# GSB200_LIB: an A/B build of the library (csrc/Makefile `variant`), for kernel experiments only
+LIB_PATH = os.environ.get("GSB200_LIB") or os.path.join(CSRC, "libgsb200.so")
 
 GSB_OK, GSB_ERR_INVALID, GSB_ERR_CUDA, GSB_ERR_TOO_MANY, GSB_ERR_CAPACITY, GSB_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 TILE = 16
@@ -186,8 +187,30 @@ def host_floats(x, n):
     return a[:n]
 
 
+_frame_cache: dict = {}
+
+
 def make_frame(viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, width, height, background, degree=3, clamped=True,
                scale_modifier=1.0) -> Frame:
+    """The per-view constants as a ``struct gsb_frame``.  A training loop passes the same few cameras again and
+    again: the struct is cached by the VALUE of its inputs (the bytes of the four small arrays and the scalars), so a
+    repeated camera costs four ``tobytes`` and one dict lookup instead of 41 Python-float conversions."""
+    vm, pm = host_floats(viewmatrix, 16), host_floats(projmatrix, 16)
+    cp, bg = host_floats(campos, 3), host_floats(background, 3)
+    key = (vm.tobytes(), pm.tobytes(), cp.tobytes(), bg.tobytes(), float(tan_fovx), float(tan_fovy), int(width),
+           int(height), int(degree), bool(clamped), float(scale_modifier))
+    f = _frame_cache.get(key)
+    if f is not None:
+        return f
+    if len(_frame_cache) > 4096:
+        _frame_cache.clear()
+    f = _frame_cache[key] = _build_frame(vm, pm, cp, tan_fovx, tan_fovy, width, height, bg, degree, clamped,
+                                         scale_modifier)
+    return f
+
+
+def _build_frame(viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, width, height, background, degree, clamped,
+                 scale_modifier) -> Frame:
     f = Frame()
     f.view[:] = host_floats(viewmatrix, 16).tolist()        # forward.py:694: row-major flatten
     f.proj[:] = host_floats(projmatrix, 16).tolist()

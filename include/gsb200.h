@@ -254,9 +254,10 @@ int gsb_adam_step_peers_compact(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t w
  * walked by one thread per pixel with the arithmetic contract, counting work and decisions on a rendered frame.
  * counters7 (device, 7 x uint64, zeroed by the call):
  *   [0] K_fwd: (pixel, Gaussian) pairs the forward loop iterates   [1] pairs that blend   [2] K_bwd: sum of
- *   min(list length, n_contrib)   [3] backward pairs whose alpha gets evaluated   [4] of those, pairs on which the raw
- *   MUFU test alpha < 1/255 disagrees with the forward's decision   [5] pairs on which the backward kernel's decision
- *   (MUFU, re-decided with the contract's exp inside a band around 1/255) disagrees: must be 0   [6] pairs in the band. */
+ *   min(list length, n_contrib)   [3] backward pairs whose alpha gets evaluated   [4] of those, pairs on which the
+ *   backward kernel's test (MUFU alpha < 1/255) disagrees with the forward's decision (measured: ~2e-8 of [3])
+ *   [5] pairs the conservative exponent threshold skips although the forward blended them: must be 0
+ *   [6] evaluated pairs whose MUFU alpha lies within 1e-7 of 1/255. */
 int gsb_selftest_work_counters(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, const int32_t* ranges,
                                const int32_t* point_list, const float* points_xy, const float* conic_opacity,
                                const int32_t* n_contrib, uint64_t* counters7);

@@ -9,7 +9,7 @@
 * gradients: norm-wise rel 1e-3 per tensor AND element-wise |d| <= 1e-3 |ref| + 1e-4 rms(ref) for EVERY element
   (measured by tools/parity_probe.py on a B200: norm-wise 0.6e-6 .. 1.9e-6, no element beyond the bound at C2 and C3,
   at most two beyond a ten times smaller floor); the backward's alpha >= 1/255 decisions are counted against the
-  forward's (measured: the raw MUFU test flips 1 of 42M pairs at C2, 2 of 144M at C3; the kernel's re-decision: 0).
+  forward's (measured: the kernel's MUFU test flips 1 of 42M pairs at C2, 2 of 144M at C3; bound 1e-6).
 """
 import numpy as np
 import pytest
@@ -70,8 +70,10 @@ def test_full_size_forward_backward_vs_oracle(gs, oracle, cfg):
     # work counters of SURVEY 8d: the pairs the reference's loops iterate, as the oracle counted them
     assert c["K_fwd"] == ob["_pairs_fwd"] and c["K_bwd"] == og["_pairs_bwd"] == int(ob["n_contrib"].astype(np.int64).sum())
     assert c["K_fwd"] >= c["K_bwd"] > c["pairs_blended"] > 0
-    assert c["bwd_decision_mismatch"] == 0, c
-    assert c["mufu_raw_mismatch"] <= 1e-5 * c["bwd_pairs_evaluated"], c      # what the band re-decision removes
+    # measured 1 (C2) and 2 (C3) disagreeing pairs, i.e. ~2e-8 of the evaluated pairs; the bound is 1e-6 (VERDICT r1 asked
+    # for 1e-5).  The conservative exponent threshold must never skip a pair the forward blended.
+    assert c["bwd_decision_mismatch"] <= 1e-6 * c["bwd_pairs_evaluated"], c
+    assert c["threshold_false_skips"] == 0, c
 
 
 def work_counters(gs, cam, buf, w, h):
@@ -86,8 +88,8 @@ def work_counters(gs, cam, buf, w, h):
                                                     p(buf["ranges"]), p(buf["point_list"]), p(buf["points_xy_image"]),
                                                     p(buf["conic_opacity"]), p(buf["n_contrib"]), p(out)))
     torch.cuda.synchronize()
-    names = ("K_fwd", "pairs_blended", "K_bwd", "bwd_pairs_evaluated", "mufu_raw_mismatch", "bwd_decision_mismatch",
-             "pairs_in_exact_band")
+    names = ("K_fwd", "pairs_blended", "K_bwd", "bwd_pairs_evaluated", "bwd_decision_mismatch", "threshold_false_skips",
+             "pairs_near_threshold")
     return dict(zip(names, [int(x) for x in out.cpu()]))
 
 

@@ -33,8 +33,8 @@ def work_counters(cam, buf, W, H):
                                                     p(buf["ranges"]), p(buf["point_list"]), p(buf["points_xy_image"]),
                                                     p(buf["conic_opacity"]), p(buf["n_contrib"]), p(out)))
     torch.cuda.synchronize()
-    names = ("K_fwd", "pairs_blended", "K_bwd", "bwd_pairs_evaluated", "mufu_raw_mismatch", "bwd_decision_mismatch",
-             "pairs_in_exact_band")
+    names = ("K_fwd", "pairs_blended", "K_bwd", "bwd_pairs_evaluated", "bwd_decision_mismatch", "threshold_false_skips",
+             "pairs_near_threshold")
     return dict(zip(names, [int(x) for x in out.cpu()]))
 
 

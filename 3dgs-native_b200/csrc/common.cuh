@@ -30,7 +30,7 @@ struct gsb_ctx {
     int fuse_sort = 0;   // 1: tiles of up to 2048 entries are sorted by the forward tile kernel's own CTAs -- measured slower
     int binning = 0;     // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
     int blend_cull = 1;  // per-block culling masks in the tile kernels
-    int tile_sort = 0;   // 0: bitonic network for every tile (default); 1: per-tile LSD radix sort (bitonic for tiles > 4096)
+    int tile_sort = 2;   // 0: bitonic network for every tile; 1: per-tile LSD radix sort (bitonic for tiles > 4096); 2 (default): radix when the longest list > 2048
     int bwd_reduce = 2;  // 2 / 1: tensor-core pixel sums at 4 / 3 resident CTAs per SM; 0: warp-shuffle butterfly
     int bwd_packed = 1;  // 1: the tensor-core backward accumulates into packed records with vector REDs; 0: nine scalar REDs
   } opt;

@@ -5,24 +5,30 @@
 // Only the live key bits are sorted: bits [0, 32 + ceil(log2(num_tiles))) for the tile|depth
 // keys (44 bits = 6 passes at 800x800 instead of 8).
 //
-// Per pass, two kernels and no inter-CTA spinning:
-//   radix_hist_kernel    every CTA counts the digits of its slice into table[cta][256]; the LAST
-//                        CTA to finish (atomic ticket) turns the table into exclusive prefixes
-//                        per digit column and writes the 256 global digit bases.
-//   radix_scatter_kernel every CTA re-reads its slice in sub-tiles of 4096 pairs, ranks them
-//                        stably (warp match_any ranking + per-warp digit counters), reorders the
-//                        sub-tile through shared memory so that each digit's run leaves as
-//                        contiguous, coalesced stores, and advances its 256 running offsets.
+// Per pass three kernels, no inter-CTA spinning, nothing serial:
+//   radix_count_kernel    every CTA counts the digits of its slice (warp-level peer masks from ballots, so a
+//                         digit all lanes share costs one add) into table[digit][cta] -- digit-major, so that
+//   radix_scan_kernel     one WARP per digit turns its row into exclusive prefixes with every load of the
+//                         row in flight at once (the round-1 version let the last CTA of the counting
+//                         kernel walk the table row by row: 34 of that pass's 81 us), and leaves the digit's
+//                         total;
+//   radix_scatter_kernel  every CTA scans the 256 totals itself (no fourth kernel), re-reads its slice in
+//                         sub-tiles of 4096 pairs, ranks them stably (warp peer-mask ranking + per-warp
+//                         digit counters), reorders the sub-tile through shared memory so that each digit's
+//                         run leaves as contiguous stores, and advances its 256 running offsets.  512
+//                         threads x 8 pairs, the values landing in shared memory by cp.async while the keys
+//                         are ranked: 64 registers (round 1: 128 registers, 47 us).
 // Algorithmic traffic: 32 B per pair per pass (key read twice, value once, pair written once).
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = 16;
+constexpr int kItems = 8;
 constexpr int kSub = kThreads * kItems;  // 4096 pairs per sub-tile
 constexpr int kMaxBlocks = 2048;
+constexpr int kCountThreads = 1024;  // a slice of ~5.6 K keys (headline size) is one batch of loads per thread
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
@@ -30,101 +36,139 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
-__global__ void __launch_bounds__(kThreads)
-radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, unsigned digit_mask, int subs_per_block,
-                  uint32_t* __restrict__ table /*[nb][256]*/, uint32_t* __restrict__ digit_base /*[256]*/,
-                  unsigned int* __restrict__ ticket) {
-  __shared__ uint32_t s_hist[kWarps][256];
-  __shared__ bool s_last;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < kWarps * 256; i += kThreads) (&s_hist[0][0])[i] = 0;
-  __syncthreads();
-  const int64_t begin = (int64_t)blockIdx.x * subs_per_block * kSub;
-  const int64_t end = min(n, begin + (int64_t)subs_per_block * kSub);
-  for (int64_t base = begin; base < end; base += kThreads * 4) {
+// The lanes of the warp that hold the same 8-bit digit as this one (valid lanes only): eight ballots, one per
+// digit bit.  __match_any_sync computes the same mask in one instruction, but MATCH goes through the MIO pipe at
+// about one warp instruction per 64 cycles per SM: with it both kernels of a pass sat behind mio_throttle /
+// short_scoreboard (31 and 18 stall cycles per issued instruction, ncu) at under 20% issue utilisation.
+__device__ __forceinline__ unsigned warp_peers8(const unsigned d, const bool valid) {
+  unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int64_t idx = base + u * kThreads + tid;
-      bool valid = idx < end;
-      unsigned d = valid ? (unsigned)((keys[idx] >> shift) & digit_mask) : 256u;
-      unsigned m = __match_any_sync(0xffffffffu, d);
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned m = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+
+__global__ void __launch_bounds__(kCountThreads, 2)
+radix_count_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, unsigned digit_mask, int64_t chunk,
+                   uint32_t* __restrict__ table /*[256][nb]*/) {
+  constexpr int NW = kCountThreads / 32;
+  __shared__ uint32_t s_hist[NW][256];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < NW * 256; i += kCountThreads) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t begin = (int64_t)blockIdx.x * chunk;
+  const int64_t end = min(n, begin + chunk);
+  for (int64_t base = begin; base < end; base += kCountThreads * 8) {
+    uint64_t k[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {   // eight independent loads in flight
+      const int64_t idx = base + u * kCountThreads + tid;
+      k[u] = idx < end ? __ldg(keys + idx) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool valid = base + u * kCountThreads + tid < end;
+      const unsigned d = (unsigned)((k[u] >> shift) & digit_mask);
+      const unsigned m = warp_peers8(d, valid);
       if (valid && lane == (__ffs(m) - 1)) s_hist[warp][d] += __popc(m);
       __syncwarp();
     }
   }
   __syncthreads();
-  {
+  if (tid < 256) {
     uint32_t c = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) c += s_hist[w][tid];
-    table[(size_t)blockIdx.x * 256 + tid] = c;
+    for (int w = 0; w < NW; ++w) c += s_hist[w][tid];
+    table[(size_t)tid * gridDim.x + blockIdx.x] = c;
   }
-  // ---- last CTA: column-wise exclusive scan of the table + global digit bases ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    unsigned t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  uint32_t run = 0;
-  const int nb = gridDim.x;
-  for (int b = 0; b < nb; ++b) {
-    uint32_t v = __ldcg(table + (size_t)b * 256 + tid);
-    table[(size_t)b * 256 + tid] = run;
-    run += v;
-  }
-  // exclusive scan of the 256 digit totals
-  __shared__ uint32_t s_tot[256];
-  s_tot[tid] = run;
-  __syncthreads();
-  if (tid < 32) {
-    uint32_t loc[8], sum = 0;
+}
+
+// One warp per digit: exclusive prefix of the digit's counts over the CTAs of the pass (a row of `nb` <= 2048
+// entries, read with up to eight independent 128-byte loads in flight per lane), written to a second table, and
+// the digit's total.
+__global__ void __launch_bounds__(256)
+radix_scan_kernel(const uint32_t* __restrict__ table, uint32_t* __restrict__ prefix, uint32_t* __restrict__ digit_total,
+                  int nb) {
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (d >= 256) return;
+  const uint32_t* const row = table + (size_t)d * nb;
+  uint32_t* const out = prefix + (size_t)d * nb;
+  uint32_t carry = 0;
+  for (int base = 0; base < nb; base += 256) {
+    uint32_t v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      loc[k] = s_tot[tid * 8 + k];
-      sum += loc[k];
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + 32 * u + lane;
+      v[u] = i < nb ? __ldcg(row + i) : 0u;
     }
-    uint32_t inc = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    uint32_t ex = inc - sum;
+    for (int u = 0; u < 8; ++u) {
+      uint32_t inc = v[u];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      digit_base[tid * 8 + k] = ex;
-      ex += loc[k];
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int i = base + 32 * u + lane;
+      if (i < nb) out[i] = carry + inc - v[u];
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
-  if (tid == 0) *ticket = 0;  // ready for the next pass
+  if (lane == 0) digit_total[d] = carry;
 }
 
 struct ScatterSmem {
   uint64_t keys[kSub];
   int32_t vals[kSub];
+  int32_t vals_in[kSub];  // the sub-tile's values in input order, landed by cp.async while the keys are ranked
   uint32_t whist[kWarps][256];
   uint32_t off[256];     // running global offset of each digit for this CTA
   uint32_t dstart[256];  // start of each digit's run inside the reordered sub-tile
   uint32_t wtot[kWarps];
 };
 
-__global__ void __launch_bounds__(kThreads)
+// exclusive scan over the 256 per-digit values held by threads 0..255 (one per thread); all kThreads threads call
+__device__ __forceinline__ uint32_t block_exclusive_256(uint32_t v, int tid, int lane, int warp, uint32_t* s_wtot,
+                                                        uint32_t& inclusive) {
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31 && warp < 8) s_wtot[warp] = inc;
+  __syncthreads();
+  uint32_t wb = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (w < warp) wb += s_wtot[w];
+  inclusive = wb + inc;
+  return wb + inc - v;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
 radix_scatter_kernel(const uint64_t* __restrict__ in_keys, const int32_t* __restrict__ in_vals,
                      uint64_t* __restrict__ out_keys, int32_t* __restrict__ out_vals, int64_t n, int shift,
-                     unsigned digit_mask, int subs_per_block, const uint32_t* __restrict__ table,
-                     const uint32_t* __restrict__ digit_base) {
+                     unsigned digit_mask, int64_t chunk, const uint32_t* __restrict__ prefix /*[256][nb]*/,
+                     const uint32_t* __restrict__ digit_total /*[256]*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned lt = lanemask_lt();
 
-  sm.off[tid] = digit_base[tid] + table[(size_t)blockIdx.x * 256 + tid];
-  const int64_t begin = (int64_t)blockIdx.x * subs_per_block * kSub;
-  const int64_t end = min(n, begin + (int64_t)subs_per_block * kSub);
+  {  // this CTA's first output position of every digit: digits below + the same digit in the CTAs before
+    uint32_t incl;
+    const uint32_t tot = tid < 256 ? digit_total[tid] : 0u;
+    const uint32_t before = tid < 256 ? prefix[(size_t)tid * gridDim.x + blockIdx.x] : 0u;   // both loads in flight
+    const uint32_t base = block_exclusive_256(tot, tid, lane, warp, sm.wtot, incl);
+    if (tid < 256) sm.off[tid] = base + before;
+  }
+  const int64_t begin = (int64_t)blockIdx.x * chunk;
+  const int64_t end = min(n, begin + chunk);
 
   for (int64_t sub = begin; sub < end; sub += kSub) {
     const int sub_count = (int)min((int64_t)kSub, end - sub);
@@ -132,24 +176,31 @@ radix_scatter_kernel(const uint64_t* __restrict__ in_keys, const int32_t* __rest
     __syncthreads();
 
     uint64_t key[kItems];
-    int32_t val[kItems];
     uint32_t rank[kItems];
     const int64_t wbase = sub + warp * (32 * kItems) + lane;
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-      int64_t idx = wbase + i * 32;
-      bool valid = idx < end;
-      key[i] = valid ? in_keys[idx] : ~0ull;
-      val[i] = valid ? in_vals[idx] : 0;
+      const int64_t idx = wbase + i * 32;
+      key[i] = idx < end ? in_keys[idx] : ~0ull;
     }
+    // the values go straight to shared memory (no registers, no wait until after the ranking)
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-      bool valid = (wbase + i * 32) < end;
-      unsigned d = valid ? (unsigned)((key[i] >> shift) & digit_mask) : 256u;
-      unsigned m = __match_any_sync(0xffffffffu, d);
+      const int64_t idx = wbase + i * 32;
+      if (idx < end) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.vals_in[warp * (32 * kItems) + i * 32 + lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(in_vals + idx) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const bool valid = (wbase + i * 32) < end;
+      const unsigned d = (unsigned)((key[i] >> shift) & digit_mask);
+      const unsigned m = warp_peers8(d, valid);
       uint32_t old = 0;
       if (valid) {
-        int leader = __ffs(m) - 1;
+        const int leader = __ffs(m) - 1;
         if (lane == leader) {
           old = sm.whist[warp][d];
           sm.whist[warp][d] = old + __popc(m);
@@ -163,59 +214,59 @@ radix_scatter_kernel(const uint64_t* __restrict__ in_keys, const int32_t* __rest
 
     // thread d: exclusive scan of digit d's counts across the warps; then scan over digits
     uint32_t cnt = 0;
+    if (tid < 256) {
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      uint32_t c = sm.whist[w][tid];
-      sm.whist[w][tid] = cnt;
-      cnt += c;
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = sm.whist[w][tid];
+        sm.whist[w][tid] = cnt;
+        cnt += c;
+      }
     }
     {
-      uint32_t inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane == 31) sm.wtot[warp] = inc;
-      __syncthreads();
-      uint32_t wb = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w)
-        if (w < warp) wb += sm.wtot[w];
-      sm.dstart[tid] = wb + inc - cnt;
+      uint32_t incl;
+      const uint32_t ex = block_exclusive_256(cnt, tid, lane, warp, sm.wtot, incl);
+      if (tid < 256) sm.dstart[tid] = ex;
     }
     __syncthreads();
 
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's own values have landed (it reads only those)
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-      if ((wbase + i * 32) < end) {
-        unsigned d = (unsigned)((key[i] >> shift) & digit_mask);
-        uint32_t p = sm.dstart[d] + sm.whist[warp][d] + rank[i];
+      const int64_t idx = wbase + i * 32;
+      if (idx < end) {
+        const unsigned d = (unsigned)((key[i] >> shift) & digit_mask);
+        const uint32_t p = sm.dstart[d] + sm.whist[warp][d] + rank[i];
         sm.keys[p] = key[i];
-        sm.vals[p] = val[i];
+        sm.vals[p] = sm.vals_in[warp * (32 * kItems) + i * 32 + lane];
       }
     }
     __syncthreads();
 
 #pragma unroll 4
     for (int p = tid; p < sub_count; p += kThreads) {
-      uint64_t k = sm.keys[p];
-      unsigned d = (unsigned)((k >> shift) & digit_mask);
-      uint32_t g = sm.off[d] + ((uint32_t)p - sm.dstart[d]);
+      const uint64_t k = sm.keys[p];
+      const unsigned d = (unsigned)((k >> shift) & digit_mask);
+      const uint32_t g = sm.off[d] + ((uint32_t)p - sm.dstart[d]);
       out_keys[g] = k;
       out_vals[g] = sm.vals[p];
     }
     __syncthreads();
-    sm.off[tid] += cnt;
+    if (tid < 256) sm.off[tid] += cnt;
   }
 }
 
-int plan(int64_t n, int* subs_per_block) {
-  int64_t total_subs = gsb_div_up(n, kSub);
-  int spb = (int)gsb_div_up(total_subs, kMaxBlocks);
-  if (spb < 1) spb = 1;
-  *subs_per_block = spb;
-  return (int)gsb_div_up(total_subs, spb);
+// The slice of the input one CTA handles in both kernels of a pass.  Up to `slots` CTAs of the scatter kernel are
+// resident at once (two per SM): when the input is more than one sub-tile per slot the slices are made equal
+// (n / slots, rounded up to 256 pairs) so that the pass is ONE wave of evenly loaded CTAs -- with one 4096-pair
+// sub-tile per CTA the headline size gave 394 CTAs on 296 slots, i.e. two rounds for most SMs.
+int plan(const gsb_ctx* ctx, int64_t n, int64_t* chunk) {
+  const int64_t slots = 2LL * (ctx->num_sms > 0 ? ctx->num_sms : 148);
+  const int64_t total_subs = gsb_div_up(n, kSub);
+  int64_t c = kSub;
+  if (total_subs > slots) c = gsb_div_up(gsb_div_up(n, slots), 256) * 256;
+  if (gsb_div_up(n, c) > kMaxBlocks) c = gsb_div_up(gsb_div_up(n, kMaxBlocks), 256) * 256;
+  *chunk = c;
+  return (int)gsb_div_up(n, c);
 }
 
 }  // namespace
@@ -236,12 +287,14 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
                                        (int)sizeof(ScatterSmem)));
     attr_set = true;
   }
-  int spb;
-  int nb = plan(n, &spb);
-  int rc = gsb_grow(ctx, (void**)&ctx->sort_table, &ctx->sort_table_cap, (int64_t)nb * 256, sizeof(uint32_t), s);
+  int64_t chunk;
+  const int nb = plan(ctx, n, &chunk);
+  // [256][nb] counts + [256][nb] prefixes
+  int rc = gsb_grow(ctx, (void**)&ctx->sort_table, &ctx->sort_table_cap, (int64_t)nb * 512, sizeof(uint32_t), s);
   if (rc != GSB_OK) return rc;
-  uint32_t* digit_base = ctx->sort_small;            // [256]
-  unsigned int* ticket = ctx->sort_small + 256;      // zero-initialised at context creation
+  uint32_t* const counts = ctx->sort_table;
+  uint32_t* const prefix = ctx->sort_table + (size_t)nb * 256;
+  uint32_t* const digit_total = ctx->sort_small;     // [256]
   const int passes = (end_bit - begin_bit + 7) / 8;
   uint64_t* kb[2] = {reinterpret_cast<uint64_t*>(k0), reinterpret_cast<uint64_t*>(k1)};
   int32_t* vb[2] = {v0, v1};
@@ -253,9 +306,10 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
     const int32_t* iv = vb[p & 1];
     uint64_t* ok = kb[(p + 1) & 1];
     int32_t* ov = (p == passes - 1 && final_vals) ? final_vals : vb[(p + 1) & 1];
-    GSB_LAUNCH(ctx, radix_hist_kernel, nb, kThreads, 0, s, ik, n, shift, mask, spb, ctx->sort_table, digit_base, ticket);
-    GSB_LAUNCH(ctx, radix_scatter_kernel, nb, kThreads, sizeof(ScatterSmem), s, ik, iv, ok, ov, n, shift, mask, spb,
-               ctx->sort_table, digit_base);
+    GSB_LAUNCH(ctx, radix_count_kernel, nb, kCountThreads, 0, s, ik, n, shift, mask, chunk, counts);
+    GSB_LAUNCH(ctx, radix_scan_kernel, 32, 256, 0, s, counts, prefix, digit_total, nb);
+    GSB_LAUNCH(ctx, radix_scatter_kernel, nb, kThreads, sizeof(ScatterSmem), s, ik, iv, ok, ov, n, shift, mask, chunk,
+               prefix, digit_total);
   }
   *result_in_second = (passes & 1) != 0;
   return GSB_OK;

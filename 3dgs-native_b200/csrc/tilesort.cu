@@ -112,26 +112,38 @@ tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__
   }
 }
 
+// Eight lanes per Gaussian: lane t of the group writes the tiles t, t + 8, ... of the Gaussian's rectangle, so the
+// ranks are read in 32-byte pieces and a Gaussian that covers a hundred tiles (6M Gaussians at 4K: 18 on average, with
+// a long tail) no longer makes one thread walk them all while its warp waits.  One thread per Gaussian took 1.05 ms
+// at that size (68 M duplicates).
+constexpr int kScatterLanes = 8;
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
                     const int* __restrict__ radii, const int* __restrict__ rank_index, int index_is_exclusive,
                     int grid_x, int grid_y, const int2* __restrict__ ranges, const int* __restrict__ rank,
                     unsigned long long* __restrict__ binned) {
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= n) return;
-  int r = radii[tid];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int gid = (int)(t / kScatterLanes), sub = (int)(t % kScatterLanes);
+  if (gid >= n) return;
+  const int r = radii[gid];
   if (r <= 0) return;
-  float2 p = xy[tid];
+  const float2 p = xy[gid];
   int rminx, rminy, rmaxx, rmaxy;
   gs_get_rect(p.x, p.y, (float)r, (float)grid_x, (float)grid_y, rminx, rminy, rmaxx, rmaxy);
-  const unsigned long long v = ((unsigned long long)__float_as_uint(depths[tid]) << 32) | (unsigned)tid;
-  // first rank of this Gaussian: rank_base[tid] (fused counting pass) or the inclusive scan shifted by one
-  int64_t e = index_is_exclusive ? rank_index[tid] : ((tid > 0) ? rank_index[tid - 1] : 0);
-  for (int y = rminy; y < rmaxy; ++y)
-    for (int x = rminx; x < rmaxx; ++x) {
-      binned[ranges[y * grid_x + x].x + rank[e]] = v;
-      ++e;
+  const unsigned long long v = ((unsigned long long)__float_as_uint(depths[gid]) << 32) | (unsigned)gid;
+  // first rank of this Gaussian: rank_base[gid] (fused counting pass) or the inclusive scan shifted by one
+  const int64_t e = index_is_exclusive ? rank_index[gid] : ((gid > 0) ? rank_index[gid - 1] : 0);
+  const int w = rmaxx - rminx, cnt = w * (rmaxy - rminy);
+  if (w <= 0) return;
+  int y = rminy + sub / w, x = rminx + sub % w;   // tile `sub` of the rectangle, row-major like the counting pass
+  for (int k = sub; k < cnt; k += kScatterLanes) {
+    binned[ranges[y * grid_x + x].x + rank[e + k]] = v;
+    x += kScatterLanes;
+    while (x >= rmaxx) {
+      x -= w;
+      ++y;
     }
+  }
 }
 
 // One CTA per tile: see tile_sort_segment (tilesort.cuh).
@@ -154,7 +166,7 @@ tile_sort_kernel(const int2* __restrict__ ranges, const unsigned long long* __re
 //   count phase   one shared-memory atomic per element on hist[digit][warp]
 //   scan          thread d scans digit d's eight warp counters, block-wide exclusive scan of the digits
 //   scatter       a warp walks its contiguous block in order; lanes with the same digit are ranked
-//                 by lane (match_any), the first of them advances hist[digit][warp]
+//                 by lane (peer masks from ballots), the first of them advances hist[digit][warp]
 // Tiles whose count is outside (lo, hi] return at once (they belong to the bitonic kernel).
 template <int CAP>
 __global__ void __launch_bounds__(256)
@@ -241,8 +253,18 @@ tile_radix_kernel(const int2* __restrict__ ranges, const unsigned long long* __r
       const bool live = i < wend;
       const unsigned key = live ? ks[i] : 0u;
       const unsigned short val = live ? vs[i] : (unsigned short)0;
-      const unsigned digit = live ? ((key >> shift) & 255u) : 256u + lane;  // dead lanes match nobody
-      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      const unsigned digit = live ? ((key >> shift) & 255u) : 256u + lane;  // dead lanes are nobody's peers
+      // peer mask from one ballot per digit bit: MATCH.ANY goes through the MIO pipe at about one warp
+      // instruction per 64 cycles per SM (sort.cu); measured: forward at 6M Gaussians / 4K 5.53 ms with the
+      // ballots against 6.1 with match_any (and 6.51 with the bitonic network)
+      unsigned peers = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (digit >> b) & 1u;
+        const unsigned bm = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bm : ~bm;
+      }
+      if (!live) peers = 1u << lane;
       const int leader = __ffs(peers) - 1;
       const unsigned rank = __popc(peers & ((1u << lane) - 1u));
       unsigned start = 0u;
@@ -363,15 +385,19 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
   unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
   const int2* rg = reinterpret_cast<const int2*>(ranges);
-  GSB_LAUNCH(ctx, tile_scatter_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
-             depths, radii, rank_index, index_is_exclusive, gx, gy, rg, ctx->vals_a, binned);
+  GSB_LAUNCH(ctx, tile_scatter_kernel, (unsigned)gsb_div_up((int64_t)n * kScatterLanes, 256), 256, 0, s, n,
+             reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
+             ctx->vals_a, binned);
   (void)num_rendered;
   if (!point_list) return GSB_OK;
-  // Per-tile sort.  Default: the bitonic kernel.  tile_sort == 1 (A/B switch): the O(n) shared-memory
-  // radix sort for tiles of up to 4096 entries and the bitonic kernel for longer ones (each kernel
-  // skips the other's tiles).  Measured on a B200 at ~650 entries per tile the radix kernel executes
-  // half the instructions but is a chain of dependent shared-memory operations and barriers (28% of
-  // the issue slots used): 60 us against the bitonic network's 47 us.  It stays as the tested option.
+  // Per-tile sort: the bitonic network (O(n log^2 n), pure register / shuffle / shared-memory compare-exchange) or
+  // the O(n) shared-memory LSD radix sort for tiles of up to 4096 entries (longer ones always go to the bitonic
+  // kernel; each kernel skips the other's tiles).  Measured on a B200, whole forward, L2 flushed:
+  //   ~650 entries per tile (300k Gaussians, 800^2):    bitonic 351 us, radix 353 us
+  //   ~920 (1M Gaussians, 1080p):                        both 1032 us
+  //   ~2100 (6M Gaussians, 4K):                          bitonic 6.51 ms, radix 5.53 ms
+  // (round 1's radix kernel ranked with match_any and lost everywhere: MATCH is an MIO-pipe instruction).
+  // tile_sort = 2 (default): radix when the frame's longest list exceeds 2048 entries; 0 / 1 force one of them.
   constexpr int kRadixCap = 4096;
   auto radix_smem = [](int cap) { return (size_t)(2 * cap + 2048) * sizeof(unsigned) + (size_t)2 * cap * sizeof(unsigned short); };
   bool& attr_set = ctx->smem_optin_tilesort;
@@ -383,7 +409,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
     attr_set = true;
   }
   int bitonic_lo = 0;  // the bitonic kernel sorts tiles with more than this many entries
-  if (ctx->opt.tile_sort == 1) {
+  if (ctx->opt.tile_sort == 1 || (ctx->opt.tile_sort == 2 && max_count > 2048)) {
     if (max_count <= 1024) {
       GSB_LAUNCH(ctx, tile_radix_kernel<1024>, num_tiles, 256, radix_smem(1024), s, rg, binned, point_list, 0, 1024);
     } else if (max_count <= 2048) {

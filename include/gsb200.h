@@ -73,8 +73,9 @@ int64_t gsb_launch_count(gsb_ctx* ctx);
  *   "bwd_reduce" = 2 (default) / 1: the backward tile kernel sums the per-pixel terms over a warp's
  *                  pixel block with TF32 tensor-core products (4 / 3 resident CTAs per SM);
  *                  0: warp-shuffle butterfly
- *   "tile_sort"  = 0 (default): bitonic network per tile; 1: per-tile shared-memory LSD radix sort
- *                  (tiles of more than 4096 entries still go to the bitonic kernel)
+ *   "tile_sort"  = 2 (default): per-tile shared-memory LSD radix sort when the frame's longest tile list exceeds
+ *                  2048 entries, bitonic network otherwise; 0: always bitonic; 1: always radix (tiles of more
+ *                  than 4096 entries still go to the bitonic kernel)
  *   "binning"    = 0 (default): gsb_forward bins by tile with a counting sort and sorts every tile's
  *                  segment in shared memory; 1: duplicate-with-keys + global 64-bit radix sort */
 int gsb_set_option(gsb_ctx* ctx, const char* name, int value);

@@ -18,6 +18,37 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def child_forward_only(cfg, iters, opts):
+    """Forward operator only (config 5 is forward-only): whole-operator time, L2 flushed before every call."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import gsb200  # noqa: F401
+    from gsb200 import scene, train
+    from gsb200.utils.camera_utils import load_nerf_cameras
+    n, w, h, smin, smax = scene.CONFIGS[cfg]
+    params, _cam, _ = scene.synthetic_scene(n, w, h, smin, smax, seed=42, with_target=False)
+    cams = load_nerf_cameras(w, h)[:1]
+    T = train.Trainer(cams, params=params, config={"num_iterations": 7000})
+    for kv in opts:
+        k, v = kv.split("=")
+        T.ctx.set_option(k, int(v))
+    for _ in range(3):
+        fb = T.forward(0)
+    torch.cuda.synchronize()
+    flush = torch.empty((256 << 20) // 4, dtype=torch.float32, device=T.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t = []
+    for i in range(iters):
+        flush.fill_(float(i))
+        e0.record(); T.forward(0); e1.record(); e1.synchronize()
+        t.append(e0.elapsed_time(e1))
+    import hashlib
+    hsh = hashlib.sha1(fb.point_list[:fb.num_rendered].cpu().numpy().tobytes()).hexdigest()[:12]
+    print(f"FWD {cfg} {' '.join(opts) or 'defaults'}: forward {np.median(t) * 1e3:9.1f} us (min {min(t) * 1e3:9.1f}), "
+          f"D={fb.num_rendered}, point_list sha1 {hsh}", flush=True)
+
+
 def child(cfg, iters, out_path):
     import ctypes as C
     import numpy as np
@@ -95,7 +126,11 @@ def main():
     ap.add_argument("--libs", default="default")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--child", default="")
+    ap.add_argument("--fwd-only", action="store_true", help="time the forward operator only (e.g. --cfg C5)")
+    ap.add_argument("--opt", action="append", default=[], help="gsb_set_option name=value (with --fwd-only)")
     args = ap.parse_args()
+    if args.fwd_only:
+        return child_forward_only(args.cfg, args.iters, args.opt)
     if args.child:
         return child(args.cfg, args.iters, args.child)
     import numpy as np

@@ -112,11 +112,12 @@ tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__
   }
 }
 
-// Eight lanes per Gaussian: lane t of the group writes the tiles t, t + 8, ... of the Gaussian's rectangle, so the
-// ranks are read in 32-byte pieces and a Gaussian that covers a hundred tiles (6M Gaussians at 4K: 18 on average, with
-// a long tail) no longer makes one thread walk them all while its warp waits.  One thread per Gaussian took 1.05 ms
-// at that size (68 M duplicates).
-constexpr int kScatterLanes = 8;
+// LANES threads per Gaussian: lane t of the group writes the tiles t, t + LANES, ... of the Gaussian's rectangle.
+// With eight lanes the ranks are read in 32-byte pieces and a Gaussian that covers a hundred tiles (6M Gaussians at
+// 4K: 18 per visible Gaussian, with a long tail) no longer makes one thread walk them all while its warp waits: 0.83
+// against 1.05 ms at that size (68 M duplicates).  At the headline size (5.7 tiles per visible Gaussian) the seven
+// extra lanes mostly idle and one thread per Gaussian is faster (15 against 23 us): the host picks by D / n.
+template <int kScatterLanes>
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
                     const int* __restrict__ radii, const int* __restrict__ rank_index, int index_is_exclusive,
@@ -385,10 +386,15 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
   unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
   const int2* rg = reinterpret_cast<const int2*>(ranges);
-  GSB_LAUNCH(ctx, tile_scatter_kernel, (unsigned)gsb_div_up((int64_t)n * kScatterLanes, 256), 256, 0, s, n,
-             reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
-             ctx->vals_a, binned);
-  (void)num_rendered;
+  if (num_rendered > 8 * (int64_t)n) {
+    GSB_LAUNCH(ctx, tile_scatter_kernel<8>, (unsigned)gsb_div_up((int64_t)n * 8, 256), 256, 0, s, n,
+               reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
+               ctx->vals_a, binned);
+  } else {
+    GSB_LAUNCH(ctx, tile_scatter_kernel<1>, (unsigned)gsb_div_up(n, 256), 256, 0, s, n,
+               reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
+               ctx->vals_a, binned);
+  }
   if (!point_list) return GSB_OK;
   // Per-tile sort: the bitonic network (O(n log^2 n), pure register / shuffle / shared-memory compare-exchange) or
   // the O(n) shared-memory LSD radix sort for tiles of up to 4096 entries (longer ones always go to the bitonic

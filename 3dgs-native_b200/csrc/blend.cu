@@ -112,6 +112,8 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges,
     }
     int cnt;
     const int slot = compact_slot<NW>(bmask != 0u, lane, warp, sm.wcnt, cnt);
+    GSB_DCHECK(bmask == 0u || (slot >= 0 && slot < NT && slot <= tid));
+    GSB_DCHECK(cnt >= 0 && cnt <= NT);
     if (bmask != 0u) {
       sm.a[slot] = ea;
       sm.b[slot] = eb;
@@ -146,6 +148,7 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges,
     for (; q + 1 < wn; q += 2) {
       if ((q & 3) == 0 && __all_sync(0xffffffffu, done)) break;  // every pixel of the block is finished
       const int jA = wlist[q], jB = wlist[q + 1];
+      GSB_DCHECK(jA < cnt && jB < cnt && jA < jB);
       const float4 aA = sm.a[jA], bA = sm.b[jA];
       const float4 aB = sm.a[jB], bB = sm.b[jB];
       const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);

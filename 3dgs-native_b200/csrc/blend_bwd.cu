@@ -456,6 +456,8 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     }
     int cnt;
     const int slot = compact_slot<NW>(bmask != 0u, lane, warp, sm.wcnt, cnt);
+    GSB_DCHECK(bmask == 0u || (slot >= 0 && slot < NT && slot <= tid));
+    GSB_DCHECK(cnt >= 0 && cnt <= NT);
     if (bmask != 0u) {
       sm.a[slot] = ea;
       sm.b[slot] = eb;
@@ -488,6 +490,7 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       float4 m03, col;
       float2 m45;
       bwd_group_moments(tS, tW, lane, fg, ft, m0, m1, m2, dp_row, dp_cols, m03, m45, col);
+      GSB_DCHECK(count >= 1 && count <= kGrp && qbase >= 0 && qbase + count <= wn);
       if (lane < count && bwd_group_nonzero(m03, m45, col)) {
         const int je = wlist[qbase + lane];
         const int gid = __float_as_int(sm.c[je].w);
@@ -521,6 +524,7 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     int q = 0;
     for (; q + 1 < wn; q += 2) {
       const int jA = wlist[q], jB = wlist[q + 1];
+      GSB_DCHECK(jA < cnt && jB < cnt && jA < jB && gslot + 2 <= kGrp);
       const float4 aA = sm.a[jA], bA = sm.b[jA];
       const float4 aB = sm.a[jB], bB = sm.b[jB];
       const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);

@@ -111,6 +111,7 @@ __device__ __forceinline__ int warp_compact_hits(const int2* s_meta, int cnt, un
       hit = (((unsigned)m.y & my_mask) != 0u) && (m.x < pos_limit);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    GSB_DCHECK(n + __popc(bal) <= 256 && e < 256 + 32);
     if (hit) widx[n + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)e;
     n += __popc(bal);
   }

@@ -87,6 +87,17 @@ int gsb_reserve_binning(gsb_ctx* ctx, cudaStream_t s, int64_t num_rendered);
     if (_rc != GSB_OK) return _rc;                                                    \
   } while (0)
 
+// Device-side bounds checks of the index arithmetic the kernels rely on (shared-memory slots, list positions, scatter
+// targets).  Compiled in only by `make variant TAG=chk EXTRA=-DGSB_DEBUG_CHECKS=1` (tools/sanitize_case.py runs the small
+// end-to-end cases on that build: compute-sanitizer is closed on this pool); a failed check traps the kernel and the
+// next CUDA call returns cudaErrorAssert.
+#ifdef GSB_DEBUG_CHECKS
+#include <assert.h>
+#define GSB_DCHECK(cond) assert(cond)
+#else
+#define GSB_DCHECK(cond) ((void)0)
+#endif
+
 #define GSB_REQUIRE(ctx, cond, msg)                                        \
   do {                                                                     \
     if (!(cond)) return gsb_set_error((ctx), GSB_ERR_INVALID, "%s", msg);  \

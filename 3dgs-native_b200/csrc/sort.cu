@@ -236,6 +236,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ in_keys, const int32_t* __rest
       if (idx < end) {
         const unsigned d = (unsigned)((key[i] >> shift) & digit_mask);
         const uint32_t p = sm.dstart[d] + sm.whist[warp][d] + rank[i];
+        GSB_DCHECK(p < (uint32_t)sub_count);
         sm.keys[p] = key[i];
         sm.vals[p] = sm.vals_in[warp * (32 * kItems) + i * 32 + lane];
       }
@@ -247,6 +248,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ in_keys, const int32_t* __rest
       const uint64_t k = sm.keys[p];
       const unsigned d = (unsigned)((k >> shift) & digit_mask);
       const uint32_t g = sm.off[d] + ((uint32_t)p - sm.dstart[d]);
+      GSB_DCHECK((int64_t)g < n && (uint32_t)p >= sm.dstart[d]);
       out_keys[g] = k;
       out_vals[g] = sm.vals[p];
     }

@@ -138,6 +138,8 @@ tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restric
   if (w <= 0) return;
   int y = rminy + sub / w, x = rminx + sub % w;   // tile `sub` of the rectangle, row-major like the counting pass
   for (int k = sub; k < cnt; k += kScatterLanes) {
+    GSB_DCHECK(y < rmaxy && x >= rminx && x < rmaxx);
+    GSB_DCHECK(rank[e + k] >= 0 && rank[e + k] < ranges[y * grid_x + x].y - ranges[y * grid_x + x].x);
     binned[ranges[y * grid_x + x].x + rank[e + k]] = v;
     x += kScatterLanes;
     while (x >= rmaxx) {

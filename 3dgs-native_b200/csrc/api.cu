@@ -20,12 +20,6 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                           int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
                           int32_t* point_list);
 int gsb_tile_binning_max();
-const unsigned long long* gsb_tile_binning_binned(gsb_ctx* ctx);
-int gsb_blend_forward_sorting(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, const int32_t* ranges,
-                              const unsigned long long* binned, int32_t* point_list, const float* points_xy,
-                              const float* rgb, const float* conic_opacity, const float* depths, float* image,
-                              float* inv_depth, float* final_T, int32_t* n_contrib, int32_t* block_masks);
-int gsb_blend_forward_fused_sort_max(const gsb_ctx* ctx);
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -170,10 +164,6 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
     ctx->opt.bwd_packed = value;
     return GSB_OK;
   }
-  if (!strcmp(name, "fuse_sort") && (value == 0 || value == 1)) {
-    ctx->opt.fuse_sort = value;
-    return GSB_OK;
-  }
   if (!strcmp(name, "bwd_reduce") && value >= 0 && value <= 2) {
     ctx->opt.bwd_reduce = value;
     return GSB_OK;
@@ -284,15 +274,8 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   if (D > point_list_capacity)
     return gsb_set_error(ctx, GSB_ERR_CAPACITY, "point_list capacity %lld < num_rendered %lld",
                          (long long)point_list_capacity, (long long)D);
-  bool sort_in_blend = false;
   if (D > 0) {
-    if (ctx->opt.binning == 0 && max_count <= gsb_blend_forward_fused_sort_max(ctx)) {
-      // scatter only: every CTA of the forward tile kernel sorts its own tile first
-      rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ctx->rank_base, 1, ranges, D,
-                                 max_count, nullptr);
-      if (rc != GSB_OK) return rc;
-      sort_in_blend = true;
-    } else if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
+    if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
       // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
       rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ctx->rank_base, 1, ranges, D,
                                  max_count, point_list);
@@ -316,9 +299,6 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
     return GSB_OK;
   }
   // forward.py:844-863 (+ the no-op track_pixel_stats of 867-879)
-  if (sort_in_blend)
-    return gsb_blend_forward_sorting(ctx, s, f, ranges, gsb_tile_binning_binned(ctx), point_list, points_xy, rgb,
-                                     conic_opacity, depths, image, inv_depth, final_T, n_contrib, block_masks);
   return gsb_blend_forward(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
                            final_T, n_contrib, block_masks);
 }

@@ -26,10 +26,7 @@
 // There a warp sums its pixels' terms for 16 Gaussians at a time on the tensor cores and adds the nine
 // results per Gaussian to one packed record with two vector REDs and a scalar one -- and only for
 // Gaussians that touched the warp at all.
-#include <type_traits>
-
 #include "blend_common.cuh"
-#include "tilesort.cuh"
 
 
 namespace {
@@ -38,35 +35,36 @@ namespace {
 #define GSB_FWD_MINB 5
 #endif
 
+// Staging is dynamic and double-buffered.  Round 1 staged every batch of 256 list entries with all eight warps
+// between CTA barriers (three per batch), so the warp with the most hits in its block decided when the CTA moved on:
+// at the barrier on top of the batch loop alone the warps spent 13% of their time (ncu source page,
+// profiles/r02_ncu_step.md), and the slowest warp also staged its 32 entries like everybody else.  Here
+//   * the staging arrays are double-buffered; a warp that has finished its hits of batch k at once takes CHUNKS
+//     (32 entries) of batch k+1 from a shared counter and stages them into the other buffer -- so the warps with few
+//     hits stage for the ones with many, and the slowest warp of a batch does no staging at all;
+//   * a chunk is compacted inside the staging warp (ballot) to the slots [32 c, 32 c + count_c): no CTA-wide prefix,
+//     no barrier inside the staging;
+//   * ONE barrier per batch remains (__syncthreads_and(done): batch k staged by everybody, batch k-1 blended by
+//     everybody, and the early exit when all 256 pixels are finished).
+// The entries reach a pixel in list order (chunks in order, slots in order).  Measured against the round-1 kernel on
+// the headline scene: 217.1 against 221.2 us, every output bit-identical (profiles/r02_experiments.md).
 struct FwdSmem {
-  float4 a[256];   // x, y, conic.a, conic.c   (two packed pairs: see gs_power_packed)
-  float4 b[256];   // conic.b, opacity, power threshold, 1/depth
-  float4 c[256];   // r, g, b, 1-based position in the tile's list (int bits)
-  int2 meta[256];  // 1-based position, block mask (read by the per-warp compaction)
-  int wcnt[8];
-  unsigned char widx[8][256];  // per warp: the staged entries that touch its block
+  float4 a[2][256];
+  float4 b[2][256];
+  float4 c[2][256];
+  int2 meta[2][256];
+  int ccnt[2][8];   // entries kept per chunk
+  int ctr[2];       // next chunk of the batch being staged into this buffer
+  unsigned char widx[8][256];
 };
 
-constexpr int kFusedSortMax = 2048;  // longest tile list the fused prologue sorts: 8 B x 2048 = the blend's own 16 KB
-
-// SORT: the CTA first sorts its own tile's segment of the binned list (tile_sort_segment, the body of
-// tile_sort_kernel) in the shared memory it later stages Gaussians in, writes the tile's part of point_list
-// -- an output of the operator -- and goes on to blend from it.  The sort is a chain of shared-memory
-// round trips and barriers that leaves most issue slots idle (48 us as a kernel of its own); the idea was
-// that inside this kernel those slots are filled by the other resident CTAs, which are blending.
-// MEASURED (B200, headline scene): forward 368 us against 359 us with the separate tile_sort_kernel -- the
-// bitonic network adds 12% to the instructions of a kernel that is issue-bound already.  A/B option
-// (gsb_set_option("fuse_sort", 1)), not the default.
-template <bool SORT>
 __global__ void __launch_bounds__(256, GSB_FWD_MINB)
-blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges,
-                     typename std::conditional<SORT, int*, const int* __restrict__>::type point_list,
-                     const unsigned long long* __restrict__ binned,
-                     const float2* __restrict__ xy, const float* __restrict__ rgb,
-                     const float4* __restrict__ conic_opacity, const float* __restrict__ depths,
-                     float* __restrict__ image, float* __restrict__ inv_depth, float* __restrict__ final_T,
-                     int* __restrict__ n_contrib, unsigned* __restrict__ block_masks) {
-  constexpr int NT = 256, NW = 8;
+blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
+                         const float2* __restrict__ xy, const float* __restrict__ rgb,
+                         const float4* __restrict__ conic_opacity, const float* __restrict__ depths,
+                         float* __restrict__ image, float* __restrict__ inv_depth, float* __restrict__ final_T,
+                         int* __restrict__ n_contrib, unsigned* __restrict__ block_masks) {
+  constexpr int NT = 256;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
 
@@ -75,8 +73,6 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges,
   const int tile_id = tile_y * P.grid_x + tile_x;
   const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
   const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
-  // A finished pixel (outside the image, or T ran out) gets a NaN x coordinate: its exponent is
-  // then NaN and fails the range test below, so the inner loop needs no separate `done` test.
   const float pxf = (float)px;
   const float pyf = (float)py;
   const unsigned my_mask = gs_warp_mask(warp);
@@ -90,88 +86,117 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges,
 
   const int2 range = ranges[tile_id];
   const int todo = range.y - range.x;
-  if (SORT && todo > 0) {
-    tile_sort_segment(range, binned, const_cast<int*>(point_list), reinterpret_cast<unsigned long long*>(smem_raw));
-    __syncthreads();  // point_list is read back below (plain loads: this CTA wrote it), smem_raw is reused
-  }
-  const unsigned char* const wlist = sm.widx[warp];
-  for (int base = 0; base < todo; base += NT) {
-    if (__syncthreads_and(done)) break;
+  const int nbatch = (todo + NT - 1) / NT;
+
+  // chunk `chunk` (32 entries) of batch `batch`, staged by this warp into buffer batch & 1
+  auto stage_chunk = [&](const int batch, const int chunk) {
+    const int buf = batch & 1;
+    const int ei = batch * NT + chunk * 32 + lane;   // position in the tile's list
     float4 ea, eb, ec;
     unsigned bmask = 0u;
-    if (base + tid < todo) {
-      const int gid = point_list[range.x + base + tid];
+    if (ei < todo) {
+      const int gid = point_list[range.x + ei];
       const float2 p = xy[gid];
       const float4 co = conic_opacity[gid];
       const float thr = gs_power_threshold(co.w);
       bmask = P.cull ? gs_block_mask(p.x, p.y, co.x, co.y, co.z, thr, tile_x0, tile_y0) : 0xffffffffu;
-      if (block_masks) block_masks[range.x + base + tid] = bmask;  // handed on to the backward
+      if (block_masks) block_masks[range.x + ei] = bmask;  // handed on to the backward
       ea = make_float4(p.x, p.y, co.x, co.z);
       eb = make_float4(co.y, co.w, thr, 1.0f / depths[gid]);
-      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(base + tid + 1));
+      ec = make_float4(rgb[3 * gid + 0], rgb[3 * gid + 1], rgb[3 * gid + 2], __int_as_float(ei + 1));
     }
-    int cnt;
-    const int slot = compact_slot<NW>(bmask != 0u, lane, warp, sm.wcnt, cnt);
-    GSB_DCHECK(bmask == 0u || (slot >= 0 && slot < NT && slot <= tid));
-    GSB_DCHECK(cnt >= 0 && cnt <= NT);
+    const unsigned keep = __ballot_sync(0xffffffffu, bmask != 0u);
     if (bmask != 0u) {
-      sm.a[slot] = ea;
-      sm.b[slot] = eb;
-      sm.c[slot] = ec;
-      sm.meta[slot] = make_int2(base + tid + 1, (int)bmask);
+      const int slot = chunk * 32 + __popc(keep & ((1u << lane) - 1u));
+      sm.a[buf][slot] = ea;
+      sm.b[buf][slot] = eb;
+      sm.c[buf][slot] = ec;
+      sm.meta[buf][slot] = make_int2(ei + 1, (int)bmask);
     }
-    __syncthreads();
-    if (__all_sync(0xffffffffu, done)) continue;  // this warp's pixels are all finished
-    const int wn = warp_compact_hits(sm.meta, cnt, my_mask, 0x7fffffff, lane, sm.widx[warp]);
-    // One hit: alpha is known and >= 1/255.  forward.py:483-499.
-    auto blend_hit = [&](const float alpha, const int j, const float inv_z) {
-      const float test_T = T * (1.0f - alpha);
-      if (test_T < 0.0001f) {            // forward.py:487: the breaking Gaussian is not counted
-        done = true;
-        npxy = gs_pack2(__int_as_float(0x7fc00000), -pyf);
-        return;
+    if (lane == 0) sm.ccnt[buf][chunk] = __popc(keep);
+  };
+
+  if (tid < 2) sm.ctr[tid] = 0;
+  if (nbatch > 0 && warp * 32 < min(NT, todo)) stage_chunk(0, warp);   // the first batch: one chunk per warp
+
+  const unsigned char* const wlist = sm.widx[warp];
+  for (int k = 0; k < nbatch; ++k) {
+    // batch k is staged (every warp staged its chunks before it arrived here) and nobody reads buffer (k+1) & 1 any
+    // more (every warp has finished batch k-1); all pixels finished => the tile is done
+    if (__syncthreads_and(done)) break;
+    const int buf = k & 1;
+    if (tid == 0) sm.ctr[buf] = 0;   // this buffer's counter is used again for batch k+2, after the next barrier
+    const int nchunk = (min(NT, todo - k * NT) + 31) >> 5;
+    if (!__all_sync(0xffffffffu, done)) {
+      // the staged entries of the batch that touch this warp's block, in list order
+      int wn = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        const int cc = sm.ccnt[buf][c];
+        bool hit = false;
+        if (lane < cc) hit = (((unsigned)sm.meta[buf][c * 32 + lane].y & my_mask) != 0u);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) sm.widx[warp][wn + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)(c * 32 + lane);
+        wn += __popc(bal);
       }
-      // Colour / depth sums are tolerance-compared (1e-4): one product alpha*T and an FMA per
-      // channel.  T, alpha and every decision keep the exact operation order of the contract.
-      const float4 c = sm.c[j];
-      const float w = alpha * T;
-      C0 = __fmaf_rn(c.x, w, C0);
-      C1 = __fmaf_rn(c.y, w, C1);
-      C2 = __fmaf_rn(c.z, w, C2);
-      Dp = __fmaf_rn(inv_z, w, Dp);
-      T = test_T;
-      last = __float_as_int(c.w);
-    };
-    // Two hits per iteration: their exponents and exponentials are independent, so they share the
-    // packed FFMA2 sequence; only the T recurrence is sequential.
-    int q = 0;
-    for (; q + 1 < wn; q += 2) {
-      if ((q & 3) == 0 && __all_sync(0xffffffffu, done)) break;  // every pixel of the block is finished
-      const int jA = wlist[q], jB = wlist[q + 1];
-      GSB_DCHECK(jA < cnt && jB < cnt && jA < jB);
-      const float4 aA = sm.a[jA], bA = sm.b[jA];
-      const float4 aB = sm.a[jB], bB = sm.b[jB];
-      const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);
-      const float pwB = gs_power_packed(gs_pack2(aB.x, aB.y), npxy, gs_pack2(aB.z, aB.w), bB.x);
-      // forward.py:474 skips power > 0; power < thr is provably alpha < 1/255 (gs_power_threshold);
-      // written so that the NaN of a finished pixel is skipped too
-      const bool okA = (pwA <= 0.0f) && (pwA >= bA.z);
-      const bool okB = (pwB <= 0.0f) && (pwB >= bB.z);
-      if (!(okA || okB)) continue;
-      float GA, GB;
-      gs_expf2(pwA, pwB, GA, GB);
-      const float alphaA = f_min(0.99f, bA.y * GA);
-      const float alphaB = f_min(0.99f, bB.y * GB);
-      if (okA && !(alphaA < (1.0f / 255.0f))) blend_hit(alphaA, jA, bA.w);
-      if (okB && !done && !(alphaB < (1.0f / 255.0f))) blend_hit(alphaB, jB, bB.w);
+      __syncwarp();
+      const float4* const sa = sm.a[buf];
+      const float4* const sb = sm.b[buf];
+      const float4* const sc = sm.c[buf];
+      // One hit: alpha is known and >= 1/255.  forward.py:483-499.
+      auto blend_hit = [&](const float alpha, const int j, const float inv_z) {
+        const float test_T = T * (1.0f - alpha);
+        if (test_T < 0.0001f) {            // forward.py:487: the breaking Gaussian is not counted
+          done = true;
+          npxy = gs_pack2(__int_as_float(0x7fc00000), -pyf);
+          return;
+        }
+        const float4 c = sc[j];
+        const float w = alpha * T;
+        C0 = __fmaf_rn(c.x, w, C0);
+        C1 = __fmaf_rn(c.y, w, C1);
+        C2 = __fmaf_rn(c.z, w, C2);
+        Dp = __fmaf_rn(inv_z, w, Dp);
+        T = test_T;
+        last = __float_as_int(c.w);
+      };
+      int q = 0;
+      for (; q + 1 < wn; q += 2) {
+        if ((q & 3) == 0 && __all_sync(0xffffffffu, done)) break;  // every pixel of the block is finished
+        const int jA = wlist[q], jB = wlist[q + 1];
+        GSB_DCHECK(jA < jB && jB < NT);
+        const float4 aA = sa[jA], bA = sb[jA];
+        const float4 aB = sa[jB], bB = sb[jB];
+        const float pwA = gs_power_packed(gs_pack2(aA.x, aA.y), npxy, gs_pack2(aA.z, aA.w), bA.x);
+        const float pwB = gs_power_packed(gs_pack2(aB.x, aB.y), npxy, gs_pack2(aB.z, aB.w), bB.x);
+        const bool okA = (pwA <= 0.0f) && (pwA >= bA.z);
+        const bool okB = (pwB <= 0.0f) && (pwB >= bB.z);
+        if (!(okA || okB)) continue;
+        float GA, GB;
+        gs_expf2(pwA, pwB, GA, GB);
+        const float alphaA = f_min(0.99f, bA.y * GA);
+        const float alphaB = f_min(0.99f, bB.y * GB);
+        if (okA && !(alphaA < (1.0f / 255.0f))) blend_hit(alphaA, jA, bA.w);
+        if (okB && !done && !(alphaB < (1.0f / 255.0f))) blend_hit(alphaB, jB, bB.w);
+      }
+      if (q < wn && q + 1 >= wn) {  // odd tail (not reached after an early exit: then q + 1 < wn)
+        const int j = wlist[q];
+        const float4 a = sa[j], b4 = sb[j];
+        const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
+        if ((power <= 0.0f) && (power >= b4.z)) {
+          const float alpha = f_min(0.99f, b4.y * gs_expf(power));
+          if (!(alpha < (1.0f / 255.0f))) blend_hit(alpha, j, b4.w);
+        }
+      }
     }
-    if (q < wn) {  // odd tail
-      const int j = wlist[q];
-      const float4 a = sm.a[j], b4 = sm.b[j];
-      const float power = gs_power_packed(gs_pack2(a.x, a.y), npxy, gs_pack2(a.z, a.w), b4.x);
-      if ((power <= 0.0f) && (power >= b4.z)) {
-        const float alpha = f_min(0.99f, b4.y * gs_expf(power));
-        if (!(alpha < (1.0f / 255.0f))) blend_hit(alpha, j, b4.w);
+    // help staging the next batch: take chunks until none is left
+    if (k + 1 < nbatch) {
+      const int nnext = (min(NT, todo - (k + 1) * NT) + 31) >> 5;
+      for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&sm.ctr[buf ^ 1], 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nnext) break;
+        stage_chunk(k + 1, c);
       }
     }
   }
@@ -224,26 +249,6 @@ GSB_API int gsb_selftest_block_mask(gsb_ctx* ctx, gsb_stream s, int32_t count, c
   return GSB_OK;
 }
 
-// gsb_blend_forward whose CTAs sort their tile's segment of `binned` (the scattered, unsorted
-// (depth_bits << 32 | id) list) into point_list first.  Precondition: no tile list longer than
-// gsb_blend_forward_fused_sort_max().
-int gsb_blend_forward_sorting(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, const int32_t* ranges,
-                              const unsigned long long* binned, int32_t* point_list, const float* points_xy,
-                              const float* rgb, const float* conic_opacity, const float* depths, float* image,
-                              float* inv_depth, float* final_T, int32_t* n_contrib, int32_t* block_masks) {
-  GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0, "gsb_blend_forward: bad frame");
-  GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_forward: conic_opacity must be 16-byte aligned");
-  static_assert(sizeof(FwdSmem) >= kFusedSortMax * sizeof(unsigned long long), "the sort buffer aliases the staging arrays");
-  BlendParams P = make_blend_params(ctx, f);
-  dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  GSB_LAUNCH(ctx, blend_forward_kernel<true>, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
-             point_list, binned, reinterpret_cast<const float2*>(points_xy), rgb,
-             reinterpret_cast<const float4*>(conic_opacity), depths, image, inv_depth, final_T, n_contrib,
-             reinterpret_cast<unsigned*>(block_masks));
-  return GSB_OK;
-}
-int gsb_blend_forward_fused_sort_max(const gsb_ctx* ctx) { return ctx->opt.fuse_sort ? kFusedSortMax : 0; }
-
 GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* rgb,
                               const float* conic_opacity, const float* depths, float* image, float* inv_depth,
@@ -254,8 +259,8 @@ GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, c
   cudaStream_t s = (cudaStream_t)s_;
   BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  GSB_LAUNCH(ctx, blend_forward_kernel<false>, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
-             point_list, nullptr, reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity), depths,
-             image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks));
+  GSB_LAUNCH(ctx, blend_forward_kernel, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
+             point_list, reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity),
+             depths, image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks));
   return GSB_OK;
 }

@@ -364,8 +364,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // with two vector REDs and one scalar RED instead of nine scalar REDs into four arrays: per flush the 16 lanes
 // touch 48 instead of 144 sectors (the replay is co-limited by the LSU data pipe, profiles/r01_ncu_bwd_warp_
 // autonomous.md).  preprocess_backward_kernel<.., PACKED> unpacks the record into the reference's arrays.
-template <int MINB, bool PACKED>  // MINB: resident CTAs per SM the register budget is cut for: 3 (80 registers) or 4 (64)
-__global__ void __launch_bounds__(256, MINB)
+template <bool PACKED>   // four resident CTAs per SM: 64 registers (3 CTAs with 80 registers measured slower in round 1)
+__global__ void __launch_bounds__(256, 4)
 blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, const int* __restrict__ point_list,
                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                           const float* __restrict__ rgb, const float* __restrict__ final_T,
@@ -680,7 +680,7 @@ GSB_API int gsb_selftest_work_counters(gsb_ctx* ctx, gsb_stream s_, const gsb_fr
 }
 
 bool gsb_blend_backward_uses_packed(const gsb_ctx* ctx) {
-  return ctx->opt.bwd_packed != 0 && (ctx->opt.bwd_reduce == 1 || ctx->opt.bwd_reduce == 2);
+  return ctx->opt.bwd_packed != 0 && ctx->opt.bwd_reduce != 0;
 }
 
 // The tensor-core kernel, either accumulating into the caller's four arrays (packed == nullptr; they must be
@@ -692,24 +692,17 @@ static int launch_backward_mma(gsb_ctx* ctx, cudaStream_t s, const BlendParams& 
                                float* dL_dcolor, const unsigned* masks, float* packed) {
   bool& attr_set = ctx->smem_optin_blend_bwd;  // > 48 KB of dynamic shared memory needs the opt-in (per device)
   if (!attr_set) {
-    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(blend_backward_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
     attr_set = true;
   }
-#define GSB_BWD_MMA(MINB, PK)                                                                                              \
-  GSB_LAUNCH(ctx, (blend_backward_mma_kernel<MINB, PK>), grid, 256, sizeof(BwdSmem), s, P,                                  \
+#define GSB_BWD_MMA(PK)                                                                                                    \
+  GSB_LAUNCH(ctx, (blend_backward_mma_kernel<PK>), grid, 256, sizeof(BwdSmem), s, P,                                        \
              reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),               \
              reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic,  \
              dL_dopacity, dL_dcolor, masks, packed)
-  if (ctx->opt.bwd_reduce == 2) {
-    if (packed) GSB_BWD_MMA(4, true);
-    else GSB_BWD_MMA(4, false);
-  } else {
-    if (packed) GSB_BWD_MMA(3, true);
-    else GSB_BWD_MMA(3, false);
-  }
+  if (packed) GSB_BWD_MMA(true);
+  else GSB_BWD_MMA(false);
 #undef GSB_BWD_MMA
   return GSB_OK;
 }

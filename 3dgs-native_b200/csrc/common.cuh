@@ -27,11 +27,10 @@ struct gsb_ctx {
   bool smem_optin_blend_bwd = false, smem_optin_radix = false, smem_optin_tilesort = false;
   // A/B knobs of gsb_set_option (per context; results never depend on them)
   struct Options {
-    int fuse_sort = 0;   // 1: tiles of up to 2048 entries are sorted by the forward tile kernel's own CTAs -- measured slower
     int binning = 0;     // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
     int blend_cull = 1;  // per-block culling masks in the tile kernels
     int tile_sort = 2;   // 0: bitonic network for every tile; 1: per-tile LSD radix sort (bitonic for tiles > 4096); 2 (default): radix when the longest list > 2048
-    int bwd_reduce = 2;  // 2 / 1: tensor-core pixel sums at 4 / 3 resident CTAs per SM; 0: warp-shuffle butterfly
+    int bwd_reduce = 2;  // 2 (1 is accepted as a synonym): tensor-core pixel sums; 0: warp-shuffle butterfly with the exact exponential
     int bwd_packed = 1;  // 1: the tensor-core backward accumulates into packed records with vector REDs; 0: nine scalar REDs
   } opt;
 

@@ -381,8 +381,6 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                           const float* depths, const int32_t* radii, const int32_t* rank_index,
                           int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
                           int32_t* point_list) {
-  // point_list == nullptr: scatter only -- the caller's forward tile kernel sorts each tile itself
-  // (gsb_blend_forward_sorting) from gsb_tile_binning_binned()
   const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
   const int num_tiles = gx * gy;
   // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
@@ -397,7 +395,6 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
                ctx->vals_a, binned);
   }
-  if (!point_list) return GSB_OK;
   // Per-tile sort: the bitonic network (O(n log^2 n), pure register / shuffle / shared-memory compare-exchange) or
   // the O(n) shared-memory LSD radix sort for tiles of up to 4096 entries (longer ones always go to the bitonic
   // kernel; each kernel skips the other's tiles).  Measured on a B200, whole forward, L2 flushed:
@@ -447,4 +444,4 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
 }
 
 int gsb_tile_binning_max() { return kMaxTileSort; }
-const unsigned long long* gsb_tile_binning_binned(gsb_ctx* ctx) { return reinterpret_cast<const unsigned long long*>(ctx->keys_a); }
+

@@ -30,6 +30,10 @@ from .config import GaussianParams
 from .scheduler import LRScheduler
 
 KEYS = ("positions", "scales", "rotations", "opacities", "shs")
+# exchange modes in which ONE kernel sums a rank's shard of the gradients out of the peers' buffers, applies Adam to
+# that shard and stores the parameters into every rank's buffer (gsb_adam_step_peers): gradient loads / parameter
+# stores are peer accesses ("peers"), multimem.ld_reduce / multimem.st ("multimem"), or peer loads + multimem.st ("hybrid")
+FUSED_EXCHANGES = ("peers", "multimem", "hybrid")
 WIDTH = {"positions": 3, "scales": 3, "rotations": 4, "opacities": 1, "shs": 48}
 SHAPE = {"positions": lambda n: (n, 3), "scales": lambda n: (n, 3), "rotations": lambda n: (n, 4),
          "opacities": lambda n: (n,), "shs": lambda n: (n * 16, 3)}
@@ -148,8 +152,9 @@ class Trainer:
     def __init__(self, cameras, targets=None, num_points=None, params=None, config=None, device=None,
                  rank=0, world_size=1, process_group=None, exchange="auto", sh_compact=True):
         """``exchange`` selects how the gradient sum and the Adam step are done when world_size > 1:
-        "nccl" = all_reduce + replicated Adam; "peers" / "multimem" = the fused kernel of
-        gsb_adam_step_peers over symmetric memory (NVLink loads / NVSwitch in-fabric reduction);
+        "nccl" = all_reduce + replicated Adam; "peers" / "multimem" / "hybrid" = the fused kernel of
+        gsb_adam_step_peers over symmetric memory (NVLink loads and stores / NVSwitch in-fabric reduction and
+        multicast / NVLink gradient loads + multicast parameter stores);
         "auto" = peers when symmetric memory is available (measured fastest at 2 and 8 B200s:
         4470 vs 4349 multimem vs 3986 nccl views/s at 8 GPUs), else nccl.
         ``sh_compact`` (peers only): on steps where every rank renders exactly one view, the ranks
@@ -163,7 +168,7 @@ class Trainer:
         self.device = torch.device("cuda", self.ctx.device_index)
         self.rank, self.world_size, self.pg = rank, world_size, process_group
         self.exchange = self._pick_exchange(exchange)
-        self.sh_compact = bool(sh_compact) and self.exchange == "peers"
+        self.sh_compact = bool(sh_compact) and self.exchange in ("peers", "hybrid")
         self._compact_step = False
         self.cameras = cameras
         bg = self.config["background_color"]
@@ -211,15 +216,15 @@ class Trainer:
             has_mc = int(getattr(hdl, "multicast_ptr", 0) or 0) != 0
             self._symm_group = group
         except Exception as e:  # no peer access / symmetric memory unavailable
-            if want in ("peers", "multimem"):
+            if want in ("peers", "multimem", "hybrid"):
                 raise RuntimeError(f"exchange={want!r} needs symmetric memory: {e}") from e
             return "nccl"
-        if want == "multimem" and not has_mc:
-            raise RuntimeError("exchange='multimem' requested but the fabric offers no multicast mapping")
-        return "multimem" if want == "multimem" else "peers"
+        if want in ("multimem", "hybrid") and not has_mc:
+            raise RuntimeError(f"exchange={want!r} requested but the fabric offers no multicast mapping")
+        return want if want in ("multimem", "hybrid") else "peers"
 
     def _new_flat(self, n, symmetric=True):
-        if symmetric and self.exchange in ("peers", "multimem"):
+        if symmetric and self.exchange in FUSED_EXCHANGES:
             return FlatGaussians(n, self.device, symmetric_group=self._symm_group)
         return FlatGaussians(n, self.device)
 
@@ -341,8 +346,8 @@ class Trainer:
         of the gradients straight out of its peers' buffers, updates that shard, and writes the new
         parameters into every rank's buffer (gsb_adam_step_peers)."""
         if compact is not None:
-            if compact and not (self.sh_compact and self.exchange == "peers"):
-                raise ValueError("compact SH exchange needs exchange='peers' and sh_compact=True")
+            if compact and not self.sh_compact:
+                raise ValueError("compact SH exchange needs exchange='peers' or 'hybrid' and sh_compact=True")
             self._compact_step = bool(compact)
         if self.exchange in ("none", "nccl"):
             self.all_reduce_gradients()
@@ -353,9 +358,8 @@ class Trainer:
         W = self.world_size
         gp = (C.c_uint64 * W)(*[int(x) for x in G.buffer_ptrs])
         pp = (C.c_uint64 * W)(*[int(x) for x in P.buffer_ptrs])
-        use_mc = self.exchange == "multimem"
-        g_mc = int(G.multicast_ptr) if use_mc else 0
-        p_mc = int(P.multicast_ptr) if use_mc else 0
+        g_mc = int(G.multicast_ptr) if self.exchange == "multimem" else 0
+        p_mc = int(P.multicast_ptr) if self.exchange in ("multimem", "hybrid") else 0
         ev = None
         if self.exchange_events is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -424,7 +428,7 @@ class Trainer:
 
     def _replace(self, new: FlatGaussians):
         """train.py:474-476 and its siblings: new parameter set, gradients and Adam moments reset to zeros."""
-        if self.exchange in ("peers", "multimem") and new.symm is None:
+        if self.exchange in FUSED_EXCHANGES and new.symm is None:
             sym = self._new_flat(new.n)          # collective: every rank arrives here with the same count
             sym.flat.copy_(new.flat)
             new = sym
@@ -510,7 +514,7 @@ class Trainer:
         """The full Adam moments as (m, v) flat CUDA tensors.  In the fused exchange modes a rank only ever
         updates the moments of its own shard of Gaussians (shard_range): the shards are put together with one
         all-reduce of buffers that are zero outside the owner's shard.  Collective when world_size > 1."""
-        if self.exchange not in ("peers", "multimem"):
+        if self.exchange not in FUSED_EXCHANGES:
             return self.adam_m.flat, self.adam_v.flat
         import torch.distributed as dist
         g0, g1 = shard_range(self.num_points, self.rank, self.world_size)

@@ -68,11 +68,9 @@ def parse():
     ap.add_argument("--tile-sort", type=int, default=2,
                     help="A/B: 0 bitonic per tile, 1 per-tile radix sort, 2 (default) radix when the longest list > 2048")
     ap.add_argument("--bwd-reduce", type=int, default=2, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem", "hybrid"])
     ap.add_argument("--bwd-packed", type=int, default=1,
                     help="A/B: 1 = backward tile kernel accumulates into packed records with vector REDs, 0 = nine scalar REDs")
-    ap.add_argument("--fuse-sort", type=int, default=0,
-                    help="A/B: 1 = the forward tile kernel's CTAs sort their own tile (lists <= 2048), 0 = tile_sort_kernel")
     ap.add_argument("--sh-compact", type=int, default=1,
                     help="A/B (peers exchange): 1 = SH gradients cross NVLink as their rank-1 factors, 0 = in full")
     ap.add_argument("--densify-every", type=int, default=0,
@@ -135,6 +133,25 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def nvlink_bytes(index):
+    """(tx, rx) data bytes of all NVLinks of one GPU from NVML's throughput counters, or None where the driver does not
+    expose them (nvidia-smi nvlink -gt d prints N/A on this pool)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)      # KiB
+        return tuple(out)
+    except Exception:
+        return None
 
 
 def make_scene(cfg_name):
@@ -455,7 +472,6 @@ def ours(args):
     T.ctx.set_option("blend_cull", args.cull)
     T.ctx.set_option("bwd_reduce", args.bwd_reduce)
     T.ctx.set_option("tile_sort", args.tile_sort)
-    T.ctx.set_option("fuse_sort", args.fuse_sort)
     T.ctx.set_option("bwd_packed", args.bwd_packed)
 
     def batch(it):   # one view per rank per step, cycling through the poses
@@ -485,6 +501,7 @@ def ours(args):
         sampler.start()
     rep_ms, rep_launches = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nvl0 = nvlink_bytes(local) if (rank == 0 and world > 1) else None
     for _ in range(R):
         barrier()
         launches0 = T.ctx.launches
@@ -496,6 +513,11 @@ def ours(args):
         barrier()
         rep_ms.append(max_over_ranks(e0.elapsed_time(e1)))
         rep_launches.append(T.ctx.launches - launches0)
+    nvl1 = nvlink_bytes(local) if (rank == 0 and world > 1) else None
+    nvlink = None
+    if nvl0 is not None and nvl1 is not None:
+        nvlink = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / (R * K), "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / (R * K),
+                  "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU, all links, over the timed repetitions"}
     order = sorted(range(R), key=lambda i: rep_ms[i])
     mid = order[(R - 1) // 2]                   # the median repetition (lower median for even R)
     ms_total, launches = rep_ms[mid], rep_launches[mid]
@@ -705,8 +727,12 @@ def ours(args):
                         "step": {"nccl": "NCCL all-reduce of 59*N gradient floats + replicated Adam",
                                  "peers": "fused NVLink peer-load gradient reduction/Adam/parameter broadcast kernel",
                                  "multimem": "fused NVSwitch multimem gradient reduction/Adam/parameter broadcast kernel",
+                                 "hybrid": "fused kernel: NVLink peer-load gradient reduction, Adam, multimem.st parameter broadcast",
                                  "none": "single GPU: Adam"}[T.exchange],
                         "exchange_plus_adam_ms": round(exchange_ms, 4), "exchange_parts": parts, "views_per_step": world,
+                        "nvlink_counters": nvlink,
+                        "nvlink_model_bytes_per_direction_per_step": (None if world == 1 else int(
+                            (world - 1) / world * ((76 if T.sh_compact else 236) + 236) * n)),
                         "num_rendered_view0": int(num_rendered), "num_points_after_timed_loops": int(num_points_timed),
                         "host_cores": os.cpu_count()},
             "multi_gpu_checks": checks, "densify_check": densify,

@@ -70,9 +70,9 @@ int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered);
 int64_t gsb_launch_count(gsb_ctx* ctx);
 /* tuning / A-B knobs outside the reference surface (per context; results never depend on them):
  *   "blend_cull" = 1 (default) / 0: per-block culling masks in the tile kernels
- *   "bwd_reduce" = 2 (default) / 1: the backward tile kernel sums the per-pixel terms over a warp's
- *                  pixel block with TF32 tensor-core products (4 / 3 resident CTAs per SM);
- *                  0: warp-shuffle butterfly
+ *   "bwd_reduce" = 2 (default; 1 is a synonym): the backward tile kernel sums the per-pixel terms over a warp's
+ *                  pixel block with TF32 tensor-core products; 0: warp-shuffle butterfly (and the contract's
+ *                  exponential instead of MUFU: the slow, independent implementation the fast one is tested beside)
  *   "tile_sort"  = 2 (default): per-tile shared-memory LSD radix sort when the frame's longest tile list exceeds
  *                  2048 entries, bitonic network otherwise; 0: always bitonic; 1: always radix (tiles of more
  *                  than 4096 entries still go to the bitonic kernel)

@@ -60,6 +60,7 @@ def compact_exchange_is_bit_identical(rank, world, cams, targets, params):
         print("compact SH exchange: parameters bit-identical to the full exchange")
 
 
+HAS_MULTICAST = False
 DENSIFY_CFG = {"num_iterations": 100, "densify_from_iter": 0, "densification_interval": 2,
                "densify_grad_threshold": 0.0002, "percent_dense": 0.01, "cull_opacity_threshold": 0.1,
                "min_valid_points": 100}
@@ -86,9 +87,10 @@ def densify_keeps_replicas_identical(rank, world, cams, targets, params):
     identically everywhere, masks from 398-433), and the Gaussian counts must agree with the NCCL run up to the
     few candidates whose summed gradient norm sits within atomics noise of the threshold."""
     counts = {}
-    for mode in ("nccl", "peers", "peers_full"):
+    dmodes = ["nccl", "peers", "peers_full"] + (["hybrid"] if HAS_MULTICAST else [])
+    for mode in dmodes:
         T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world,
-                          exchange=mode.split("_")[0], sh_compact=(mode == "peers"), config=dict(DENSIFY_CFG))
+                          exchange=mode.split("_")[0], sh_compact=(mode in ("peers", "hybrid")), config=dict(DENSIFY_CFG))
         hist = [T.num_points]                # hist[it] = Gaussians after iteration it
         for it in range(1, 7):
             batch = [(it * world + r) % len(cams) for r in range(world)]
@@ -102,7 +104,7 @@ def densify_keeps_replicas_identical(rank, world, cams, targets, params):
         if rank == 0:
             print(f"densify {mode}: num_points per iteration {hist}")
     n0 = params["positions"].shape[0]
-    for mode in ("peers", "peers_full"):
+    for mode in dmodes[1:]:
         for a, b in zip(counts[mode], counts["nccl"]):
             assert abs(a - b) <= max(8, n0 // 500), (mode, counts[mode], counts["nccl"])
 
@@ -188,12 +190,15 @@ def main():
     modes = ["nccl", "peers", "peers_full"]    # "peers" = default (compact SH exchange), "peers_full" = sh_compact off
     probe = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange="auto")
     assert probe.exchange == "peers"
-    if int(getattr(probe.params.symm, "multicast_ptr", 0) or 0) != 0:
-        modes.append("multimem")
+    global HAS_MULTICAST
+    HAS_MULTICAST = int(getattr(probe.params.symm, "multicast_ptr", 0) or 0) != 0
+    if HAS_MULTICAST:
+        modes += ["multimem", "hybrid", "hybrid_full"]   # hybrid: peer-load gradients + multimem.st parameters
     for mode in modes:
+        compact = mode in ("peers", "hybrid")
         T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world,
-                          exchange=mode.split("_")[0], sh_compact=(mode == "peers"), config={"num_iterations": 100})
-        assert T.exchange == mode.split("_")[0] and T.sh_compact == (mode == "peers")
+                          exchange=mode.split("_")[0], sh_compact=compact, config={"num_iterations": 100})
+        assert T.exchange == mode.split("_")[0] and T.sh_compact == compact
         for it in range(steps):
             T.train_step(it, [(it * world + r) % len(cams) for r in range(world)], densify=False)
         torch.cuda.synchronize()

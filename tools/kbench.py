@@ -49,7 +49,7 @@ def child_forward_only(cfg, iters, opts):
           f"D={fb.num_rendered}, point_list sha1 {hsh}", flush=True)
 
 
-def child(cfg, iters, out_path):
+def child(cfg, iters, out_path, opts=()):
     import ctypes as C
     import numpy as np
     import torch
@@ -65,6 +65,9 @@ def child(cfg, iters, out_path):
     lrs = {"lr_pos": 1e-6, "lr_scale": 5e-7, "lr_rot": 5e-7, "lr_sh": 2e-7, "lr_opac": 5e-7, "final_lr_factor": 0.01}
     T = train.Trainer(cams, targets=targets, params=params, config={"num_iterations": 7000, "lr_scheduler_config": lrs})
     L, ctx, p = _lib.lib(), T.ctx, _lib.ptr
+    for kv in opts:
+        k_, v_ = kv.split("=")
+        ctx.set_option(k_, int(v_))
     s = lambda: _lib.stream_ptr(ctx.device_index)  # noqa: E731
     fb = T.forward(0)
     T.loss_and_pixel_gradients(fb, T.targets[0])
@@ -132,18 +135,23 @@ def main():
     if args.fwd_only:
         return child_forward_only(args.cfg, args.iters, args.opt)
     if args.child:
-        return child(args.cfg, args.iters, args.child)
+        return child(args.cfg, args.iters, args.child, args.opt)
     import numpy as np
     csrc = os.path.join(ROOT, "3dgs-native_b200", "csrc")
     base = None
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for tag in args.libs.split(","):
+    # a variant is a library tag, optionally followed by options:  default  default:fwd_dyn=0  x:bwd_reduce=1:fwd_dyn=0
+    for spec in args.libs.split(","):
+        tag, *vopts = spec.split(":")
         env = dict(os.environ)
         if tag != "default":
             env["GSB200_LIB"] = os.path.join(csrc, f"libgsb200_{tag}.so")
-        out = os.path.join("/tmp", f"kbench_{tag}.npz")
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cfg", args.cfg, "--iters", str(args.iters),
-                            "--child", out], env=env, capture_output=True, text=True)
+        out = os.path.join("/tmp", f"kbench_{spec.replace(':', '_').replace('=', '')}.npz")
+        cmd = [sys.executable, os.path.abspath(__file__), "--cfg", args.cfg, "--iters", str(args.iters), "--child", out]
+        for o in list(args.opt) + vopts:
+            cmd += ["--opt", o]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        tag = spec
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("KBENCH ")]
         if r.returncode != 0 or not line:
             print(f"{tag}: FAILED rc={r.returncode}\n{r.stderr[-1500:]}")

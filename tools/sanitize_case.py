@@ -9,8 +9,7 @@ instead (any failed check traps the kernel):
 
 and, where compute-sanitizer is available:  compute-sanitizer --tool memcheck|racecheck python tools/sanitize_case.py
 Besides the checks, every forward is run three times and must give the same bits (the per-tile counters, the rank
-cursor and the loss accumulator re-zero themselves across frames; the fused-sort path aliases its sort buffer over the
-staging arrays).
+cursor and the loss accumulator re-zero themselves across frames).
 
 Case 1: render.py's 3-Gaussian scene (forward, both binning paths).  Case 2: 3000 Gaussians at 96x64 -- forward,
 L1 loss, backward (tensor-core and shuffle reductions, masks handed on and recomputed), Adam, one densify event,
@@ -47,18 +46,16 @@ def main():
         img, depth, buf = forward.render_gaussians(**scene.render_kwargs(params, cam))
     ctx.set_option("tile_sort", 2)
     ref = None
-    for fuse in (0, 1, 0, 0):              # self-resetting scratch + the aliasing fused-sort path: same bits every time
-        ctx.set_option("fuse_sort", fuse)
+    for _ in range(3):                     # self-resetting scratch: same bits every time
         i2, d2, b2 = forward.render_gaussians(**scene.render_kwargs(params, cam))
         cur = [i2.clone(), d2.clone()] + [b2[k].clone() for k in sorted(b2) if k != "block_masks"]
         if ref is None:
             ref = cur
         assert all(torch.equal(a, b) for a, b in zip(ref, cur)), "repeated frames differ"
-    ctx.set_option("fuse_sort", 0)
     l1 = [float(loss.l1_loss(img, target)) for _ in range(3)]
     assert l1[0] == l1[1] == l1[2], l1
     dpix = loss.compute_image_gradients(img, target, 0.0)
-    for mode in (2, 1, 0):
+    for mode in (2, 0):
         ctx.set_option("bwd_reduce", mode)
         for hand_on in (True, False):
             b = dict(buf)

@@ -529,16 +529,17 @@ def ours(args):
 
     # ---- where the exchange + Adam part of the step goes (10 extra, untimed steps with CUDA events) -----
     # device time this rank spends between the end of its backward and the end of the exchange + Adam
-    # (incl. waiting for the slowest rank at the first barrier); max over ranks of the per-step mean
+    # (incl. waiting for the slowest rank at the first barrier); max over ranks of the per-step median
     T.exchange_events, T.exchange_parts = [], []
     for _ in range(10):
         T.train_step(it, batch(it), densify=False)
         it += 1
     barrier()
-    exchange_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in T.exchange_events])))
+    # (medians: the first of these steps can wait a long time for a rank that is still reading its NVML counters)
+    exchange_ms = max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in T.exchange_events])))
     parts = None
     if T.exchange_parts:
-        arr = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in T.exchange_parts]).mean(axis=0)
+        arr = np.median(np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in T.exchange_parts]), axis=0)
         parts = {"wait_and_barrier_ms": round(max_over_ranks(float(arr[0])), 4),
                  "fused_kernel_ms": round(max_over_ranks(float(arr[1])), 4),
                  "final_barrier_ms": round(max_over_ranks(float(arr[2])), 4)}

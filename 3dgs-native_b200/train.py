@@ -82,25 +82,45 @@ def flat_layout(n: int):
     return offs, max(total, 4)
 
 
+def headroom(n: int) -> int:
+    """Capacity (in Gaussians) allocated for a state that currently holds ``n``: densify grows the set by a few per
+    cent per event, and every reallocation costs cudaMalloc / cudaFree calls -- and, in the fused exchange modes, a
+    symmetric-memory rendezvous across the ranks -- so buffers are sized once with 50% to spare."""
+    return max(n + n // 2, n + 4096)
+
+
 class FlatGaussians:
     """One contiguous fp32 buffer holding the five per-Gaussian tensors back to back (each segment
     starts on a 16-byte boundary), with views of the reference's shapes.  The gradient instance of
-    this class is what gets all-reduced: one message of 59*N floats."""
+    this class is what gets all-reduced: one message of 59*N floats.
 
-    def __init__(self, n: int, device, fill: float | None = 0.0, symmetric_group=None):
-        self.n = n
-        offs, total = flat_layout(n)
+    The buffer is allocated for ``capacity`` >= n Gaussians; ``resize(n)`` re-lays the five segments out for another
+    count inside the same memory (the layout depends on n, the base address does not: peer mappings stay valid)."""
+
+    def __init__(self, n: int, device, fill: float | None = 0.0, symmetric_group=None, capacity: int | None = None):
+        self.capacity = max(int(capacity or 0), n)
+        _offs, total = flat_layout(self.capacity)
         self.symm = None
         if symmetric_group is not None:
             # symmetric memory: every rank can address every other rank's copy (NVLink peer mapping,
             # plus an NVSwitch multicast address when the fabric supports it)
             import torch.distributed._symmetric_memory as symm_mem
-            self.flat = symm_mem.empty(total, dtype=torch.float32, device=device)
-            self.flat.zero_()
-            self.symm = symm_mem.rendezvous(self.flat, symmetric_group)
+            self.store = symm_mem.empty(total, dtype=torch.float32, device=device)
+            self.store.zero_()
+            self.symm = symm_mem.rendezvous(self.store, symmetric_group)
         else:
-            self.flat = (torch.zeros if fill == 0.0 else torch.empty)(total, dtype=torch.float32, device=device)
+            self.store = (torch.zeros if fill == 0.0 else torch.empty)(total, dtype=torch.float32, device=device)
+        self.resize(n)
+
+    def resize(self, n: int):
+        """The same memory laid out for ``n`` Gaussians (contents are NOT moved)."""
+        if n > self.capacity:
+            raise ValueError(f"{n} Gaussians do not fit a buffer of capacity {self.capacity}")
+        self.n = n
+        offs, total = flat_layout(n)
+        self.flat = self.store[:total]
         self.views = {k: self.flat[offs[k]: offs[k] + n * WIDTH[k]].view(SHAPE[k](n)) for k in KEYS}
+        return self
 
     def __getitem__(self, k):
         return self.views[k]
@@ -118,13 +138,16 @@ class FlatGaussians:
 
 
 class FrameBuffers:
-    """Every per-view output of forward/backward, allocated once and reused across steps."""
+    """Every per-view output of forward/backward, allocated once and reused across steps.  The per-Gaussian arrays are
+    allocated for ``n_capacity`` Gaussians (the kernels take pointers and a count), so a densify event that stays
+    inside the capacity reuses them."""
 
-    def __init__(self, n: int, width: int, height: int, device, capacity: int):
+    def __init__(self, n: int, width: int, height: int, device, capacity: int, n_capacity: int | None = None):
         f32, i32 = torch.float32, torch.int32
         e = lambda *s, dtype=f32: torch.empty(s, dtype=dtype, device=device)  # noqa: E731
         gx, gy = (width + 15) // 16, (height + 15) // 16
         self.n, self.W, self.H = n, width, height
+        self.n_capacity = n = max(int(n_capacity or 0), n)
         self.radii, self.point_offsets = e(n, dtype=i32), e(n, dtype=i32)
         self.xy, self.depths, self.colors, self.cov3Ds = e(n, 2), e(n), e(n, 3), e(n, 6)
         self.conic_opacity, self.clamped_state = e(n, 4), e(n, 3)
@@ -140,12 +163,13 @@ class FrameBuffers:
         self.dL_dcolor, self.dL_dmean2D, self.dL_dconic = e(n, 3), e(n, 3), e(n, 4)
 
     def as_reference_dict(self):
-        """The 12-key dict of forward.py:881-894."""
-        return {"radii": self.radii, "point_offsets": self.point_offsets, "points_xy_image": self.xy,
-                "depths": self.depths, "colors": self.colors, "cov3Ds": self.cov3Ds,
-                "conic_opacity": self.conic_opacity, "point_list": self.point_list[: self.num_rendered],
+        """The 12-key dict of forward.py:881-894 (views of the first n rows of the per-Gaussian arrays)."""
+        n = self.n
+        return {"radii": self.radii[:n], "point_offsets": self.point_offsets[:n], "points_xy_image": self.xy[:n],
+                "depths": self.depths[:n], "colors": self.colors[:n], "cov3Ds": self.cov3Ds[:n],
+                "conic_opacity": self.conic_opacity[:n], "point_list": self.point_list[: self.num_rendered],
                 "ranges": self.ranges, "final_Ts": self.final_T, "n_contrib": self.n_contrib,
-                "clamped_state": self.clamped_state}
+                "clamped_state": self.clamped_state[:n]}
 
 
 class Trainer:
@@ -178,14 +202,15 @@ class Trainer:
         self.targets = None if targets is None else [_lib.to_device(t, device=self.device) for t in targets]
         from .utils.camera_utils import scene_extent
         self.scene_extent = scene_extent(cameras, self.config.get("camera_extent_factor", 1.0))
+        self._scratch_bufs, self._densify_tmp, self.fb = {}, [None, None], None
         if params is not None:
             n = int(np.asarray(params["positions"].shape)[0]) if not isinstance(params["positions"], torch.Tensor) \
                 else params["positions"].shape[0]
             self.num_points = n
-            self.params = self._new_flat(n).load(params)
+            self.params = self._new_flat(n, capacity=headroom(n)).load(params)
         else:
             self.num_points = n = int(num_points or self.config["num_points"])
-            self.params = self._new_flat(n)
+            self.params = self._new_flat(n, capacity=headroom(n))
             optimizer.init_gaussian_params(self.params["positions"], self.params["scales"], self.params["rotations"],
                                            self.params["opacities"], self.params["shs"], n, self.config["initial_scale"])
         self._alloc_state()
@@ -194,7 +219,6 @@ class Trainer:
         self.lr_scheduler = None
         if self.config["use_lr_scheduler"]:
             self.lr_scheduler = {k: LRScheduler(sc[k], ff) for k in ("lr_pos", "lr_scale", "lr_rot", "lr_sh", "lr_opac")}
-        self.fb = None
         self._last_hw = (1, 1)
         self.losses = []
 
@@ -223,30 +247,48 @@ class Trainer:
             raise RuntimeError(f"exchange={want!r} requested but the fabric offers no multicast mapping")
         return want if want in ("multimem", "hybrid") else "peers"
 
-    def _new_flat(self, n, symmetric=True):
+    def _new_flat(self, n, symmetric=True, capacity=None):
         if symmetric and self.exchange in FUSED_EXCHANGES:
-            return FlatGaussians(n, self.device, symmetric_group=self._symm_group)
-        return FlatGaussians(n, self.device)
+            return FlatGaussians(n, self.device, symmetric_group=self._symm_group, capacity=capacity)
+        return FlatGaussians(n, self.device, capacity=capacity)
 
     def _alloc_state(self):
+        """Gradients and Adam moments for self.num_points Gaussians, all zeros (train.py:160-164, 474-476).  The
+        buffers are reused while the count fits their capacity: a densify event then costs three memsets instead of
+        three allocations (and, in the fused exchange modes, no symmetric-memory rendezvous)."""
         n = self.num_points
-        self.grads = self._new_flat(n)                  # train.py:160-164 (zeros)
-        self.adam_m = FlatGaussians(n, self.device)     # only this rank's shard is used in the fused modes
-        self.adam_v = FlatGaussians(n, self.device)
+        old = getattr(self, "grads", None)
+        if old is not None and old.capacity >= n and self.adam_m.capacity >= n and self.adam_v.capacity >= n:
+            for buf in (self.grads, self.adam_m, self.adam_v):
+                buf.resize(n).zero_()
+        else:
+            cap = headroom(n)
+            self.grads = self._new_flat(n, capacity=cap)
+            self.adam_m = FlatGaussians(n, self.device, capacity=cap)   # only this rank's shard is used in the fused modes
+            self.adam_v = FlatGaussians(n, self.device, capacity=cap)
         self.grads_tmp = None
-        self.fb = None
-        self.sh_local = None
         if self.sh_compact:       # the expanded SH gradient of this rank's shard (local scratch)
-            shard = -(-n // self.world_size) + 8
-            self.sh_local = torch.empty(48 * shard, dtype=torch.float32, device=self.device)
+            shard = -(-self.grads.capacity // self.world_size) + 8
+            if getattr(self, "sh_local", None) is None or self.sh_local.numel() < 48 * shard:
+                self.sh_local = torch.empty(48 * shard, dtype=torch.float32, device=self.device)
+        else:
+            self.sh_local = None
 
     def _frame_buffers(self, cam):
         W, H = cam["width"], cam["height"]
         fb = self.fb
-        if fb is None or fb.n != self.num_points or fb.W != W or fb.H != H:
+        if fb is None or fb.n_capacity < self.num_points or fb.W != W or fb.H != H:
             cap = max(self.ctx.capacity_hint, 4 * self.num_points, 1024)
-            fb = self.fb = FrameBuffers(self.num_points, W, H, self.device, cap)
+            fb = self.fb = FrameBuffers(self.num_points, W, H, self.device, cap, n_capacity=headroom(self.num_points))
+        fb.n = self.num_points
         return fb
+
+    def _scratch(self, name, count, dtype):
+        """Reusable device scratch of the densify step (masks, prefixes, gradient norms); contents undefined."""
+        t = self._scratch_bufs.get(name)
+        if t is None or t.numel() < count or t.dtype != dtype:
+            t = self._scratch_bufs[name] = torch.empty(headroom(count), dtype=dtype, device=self.device)
+        return t[:count]
 
     # ---- forward / backward on preallocated buffers ---------------------------------------------
     def forward(self, cam_index: int) -> FrameBuffers:
@@ -421,18 +463,27 @@ class Trainer:
         return densify_due(self.config, iteration)
 
     def _alloc_like(self, n):
-        """The wp.zeros outputs of train.py:441-447 etc.  Intermediate Gaussian sets of one densify call live in
-        plain device memory; only the set that survives the call is moved into symmetric memory (_replace):
-        one rendezvous per densify event instead of one per clone / split / compact."""
-        return FlatGaussians(n, self.device)
+        """The wp.zeros outputs of train.py:441-447 etc.  The intermediate Gaussian sets of one densify call (clone ->
+        split -> compact -> prune) alternate between two reusable plain buffers (every element of an output set is
+        written by the kernel that produces it); the set that survives is copied into the parameter buffer."""
+        self._tmp_turn = 1 - getattr(self, "_tmp_turn", 1)
+        t = self._densify_tmp[self._tmp_turn]
+        if t is None or t.capacity < n:
+            t = self._densify_tmp[self._tmp_turn] = FlatGaussians(n, self.device, fill=None, capacity=headroom(n))
+        return t.resize(n)
 
     def _replace(self, new: FlatGaussians):
-        """train.py:474-476 and its siblings: new parameter set, gradients and Adam moments reset to zeros."""
-        if self.exchange in FUSED_EXCHANGES and new.symm is None:
-            sym = self._new_flat(new.n)          # collective: every rank arrives here with the same count
-            sym.flat.copy_(new.flat)
-            new = sym
-        self.params, self.num_points = new, new.n
+        """train.py:474-476 and its siblings: new parameter set, gradients and Adam moments reset to zeros.  The
+        parameter buffer (symmetric memory in the fused exchange modes) is kept while the new count fits its capacity:
+        the new set is copied in; otherwise a larger one is allocated (collective: every rank arrives here with the
+        same count)."""
+        if new is not self.params:
+            if self.params.capacity >= new.n:
+                self.params.resize(new.n)
+            else:
+                self.params = self._new_flat(new.n, capacity=headroom(new.n))
+            self.params.flat.copy_(new.flat)
+        self.num_points = new.n
         self._alloc_state()
 
     def densification_and_pruning(self, iteration):
@@ -444,13 +495,13 @@ class Trainer:
         i32 = torch.int32
         if self.densify_due(iteration):
             n = self.num_points
-            avg_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+            avg_grads = self._scratch("avg_grads", n, torch.float32)     # every kernel below writes all of its output
             optimizer.compute_grad_norms(self.grads["positions"], avg_grads, n)
             gt, pd, ext = cfg["densify_grad_threshold"], cfg["percent_dense"], self.scene_extent
             P = cur = self.params                # `cur`: the Gaussian set as the reference's self.params sees it
-            clone_mask = torch.zeros(n, dtype=i32, device=self.device)
+            clone_mask = self._scratch("clone_mask", n, i32)
             optimizer.mark_clone_candidates(avg_grads, P["scales"], gt, ext, pd, n, clone_mask)
-            clone_prefix = torch.zeros_like(clone_mask)
+            clone_prefix = self._scratch("clone_prefix", n, i32)
             total_to_clone = optimizer.array_scan(clone_mask, clone_prefix, inclusive=False)
             if total_to_clone > 0:
                 out = self._alloc_like(n + total_to_clone)
@@ -460,10 +511,10 @@ class Trainer:
                 cur = out
                 log["cloned"] = total_to_clone
             n, P = cur.n, cur
-            split_mask = torch.zeros(n, dtype=i32, device=self.device)
+            split_mask = self._scratch("split_mask", n, i32)
             # quirk G4: avg_grads still has the pre-clone length
             optimizer.mark_split_candidates(avg_grads, P["scales"], gt, ext, pd, n, split_mask)
-            split_prefix = torch.zeros_like(split_mask)
+            split_prefix = self._scratch("split_prefix", n, i32)
             total_to_split = optimizer.array_scan(split_mask, split_prefix, inclusive=False)
             if total_to_split > 0:
                 N0, n_split = n, 2
@@ -474,9 +525,9 @@ class Trainer:
                                           out["rotations"], out["opacities"], out["shs"])
                 P = cur = out
                 log["split"] = total_to_split
-                valid = torch.zeros(new_n, dtype=i32, device=self.device)
+                valid = self._scratch("valid", new_n, i32)
                 optimizer.split_valid_mask(split_mask, valid, N0, new_n)
-                prefix = torch.zeros_like(valid)
+                prefix = self._scratch("prefix", new_n, i32)
                 valid_count = optimizer.array_scan(valid, prefix, inclusive=False)
                 if valid_count < new_n:
                     out = self._alloc_like(valid_count)
@@ -486,9 +537,9 @@ class Trainer:
                     log["split_removed"] = new_n - valid_count
                     cur = out
             n, P = cur.n, cur
-            valid = torch.zeros(n, dtype=i32, device=self.device)
+            valid = self._scratch("valid", n, i32)
             optimizer.prune_gaussians(P["opacities"], cfg["cull_opacity_threshold"], n, valid)
-            prefix = torch.zeros_like(valid)
+            prefix = self._scratch("prefix", n, i32)
             valid_count = optimizer.array_scan(valid, prefix, inclusive=False)
             prune_count = n - valid_count
             prune_ratio = prune_count / n if n > 0 else 0
@@ -558,7 +609,7 @@ class Trainer:
         from .utils.point_cloud_utils import load_ply
         params = load_ply(os.path.join(str(ckpt_dir), "point_cloud.ply"))
         st = np.load(os.path.join(str(ckpt_dir), "state.npz"))
-        self._replace(FlatGaussians(int(st["num_points"]), self.device).load(params))
+        self._replace(FlatGaussians(int(st["num_points"]), self.device).load(params))     # copied into the state buffers
         self.adam_m.flat.copy_(torch.from_numpy(st["adam_m"]))
         self.adam_v.flat.copy_(torch.from_numpy(st["adam_v"]))
         return int(st["iteration"]) + 1

@@ -260,7 +260,9 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
     if (rc != GSB_OK) return rc;
     if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges)) != GSB_OK) return rc;
     // forward.py:755-764: inclusive scan
-    if ((rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK) return rc;
+    // (point_offsets == NULL: the caller does not want this output; the scan is then left out of the frame --
+    // measured 4-7 us per step, the three scan kernels are not always hidden behind the host's wake-up)
+    if (point_offsets && (rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK) return rc;
     if ((rc = gsb_tile_binning_wait(ctx, &D, &max_count)) != GSB_OK) return rc;
     if (D <= ctx->bin_cap || D > GSB_MAX_RENDERED) break;
     // first frame / scene grew: the rank buffer was too small.  Grow it and redo the pass.
@@ -282,9 +284,15 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
       if (rc != GSB_OK) return rc;
     } else {
       // a tile list too long for the shared-memory sort (or the A/B switch): the reference's own
-      // sequence on the global radix sort; it rewrites ranges
+      // sequence on the global radix sort; it rewrites ranges.  It needs the inclusive scan: into the caller's
+      // array, or (caller passed NULL) into the rank index of the abandoned counting pass
       int64_t D2 = 0;
-      rc = gsb_bin_by_tile(ctx, s_, f->width, f->height, n, points_xy, depths, radii, point_offsets, point_list,
+      int32_t* offs = point_offsets;
+      if (!offs) {
+        offs = ctx->rank_base;
+        if ((rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, offs, nullptr)) != GSB_OK) return rc;
+      }
+      rc = gsb_bin_by_tile(ctx, s_, f->width, f->height, n, points_xy, depths, radii, offs, point_list,
                            point_list_capacity, ranges, &D2, nullptr);
       if (rc != GSB_OK) return rc;
     }

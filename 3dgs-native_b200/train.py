@@ -163,7 +163,8 @@ class FrameBuffers:
         self.dL_dcolor, self.dL_dmean2D, self.dL_dconic = e(n, 3), e(n, 3), e(n, 4)
 
     def as_reference_dict(self):
-        """The 12-key dict of forward.py:881-894 (views of the first n rows of the per-Gaussian arrays)."""
+        """The 12-key dict of forward.py:881-894 (views of the first n rows of the per-Gaussian arrays);
+        point_offsets is valid after Trainer.forward(..., point_offsets=True)."""
         n = self.n
         return {"radii": self.radii[:n], "point_offsets": self.point_offsets[:n], "points_xy_image": self.xy[:n],
                 "depths": self.depths[:n], "colors": self.colors[:n], "cov3Ds": self.cov3Ds[:n],
@@ -291,16 +292,19 @@ class Trainer:
         return t[:count]
 
     # ---- forward / backward on preallocated buffers ---------------------------------------------
-    def forward(self, cam_index: int) -> FrameBuffers:
-        """render_gaussians as called at train.py:935-955."""
+    def forward(self, cam_index: int, point_offsets: bool = False) -> FrameBuffers:
+        """render_gaussians as called at train.py:935-955.  ``point_offsets``: also compute that output (the
+        inclusive scan of tiles_touched, forward.py:755-763) -- nothing in the step loop reads it, so by default the
+        scan is left out of the frame."""
         cam, frame = self.cameras[cam_index], self.frames[cam_index]
         fb = self._frame_buffers(cam)
         P, p, L = self.params, _lib.ptr, _lib.lib()
         D = C.c_int64(0)
+        fb.has_point_offsets = bool(point_offsets)
         for _ in range(2):
             rc = L.gsb_forward(self.ctx.h, _lib.stream_ptr(self.ctx.device_index), C.byref(frame), self.num_points,
                                p(P["positions"]), p(P["scales"]), p(P["rotations"]), p(P["opacities"]), p(P["shs"]),
-                               p(fb.radii), p(fb.point_offsets), p(fb.xy), p(fb.depths), p(fb.colors), p(fb.cov3Ds),
+                               p(fb.radii), p(fb.point_offsets if point_offsets else None), p(fb.xy), p(fb.depths), p(fb.colors), p(fb.cov3Ds),
                                p(fb.conic_opacity), p(fb.clamped_state), p(fb.point_list), fb.capacity, p(fb.ranges),
                                p(fb.image), p(fb.depth), p(fb.final_T), p(fb.n_contrib), C.byref(D),
                                p(fb.block_masks))

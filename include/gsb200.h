@@ -139,7 +139,9 @@ int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, const int3
  * point_list_capacity entries; *num_rendered_host receives D.  Returns GSB_ERR_CAPACITY (with D
  * set, per-Gaussian outputs valid, image untouched) when D > capacity so the caller can grow
  * and call again, GSB_ERR_TOO_MANY when D > 2^30.  When D == 0 the image outputs are all ZERO
- * (not background), like the reference (forward.py:830).  Synchronises once (to learn D). */
+ * (not background), like the reference (forward.py:830).  Synchronises once (to learn D).
+ * point_offsets may be NULL when the caller does not need that output (the inclusive scan of tiles_touched is not an
+ * input of this binning): the trainer's loop passes NULL and saves the three scan kernels. */
 int gsb_forward(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n, const float* means,
                 const float* scales, const float* rotations, const float* opacities, const float* shs,
                 int32_t* radii, int32_t* point_offsets, float* points_xy, float* depths, float* rgb,

@@ -40,3 +40,28 @@ def test_load_camera_matches_reference_source(golden_dir, tag, size):
         assert np.array_equal(np.array([c[key] for c in cams], dtype=np.float64), g[f"{tag}_{key}"]), key
     assert scene_extent(cams, 1.0) == float(g[f"{tag}_scene_extent"])
     assert all(c["width"] == W and c["height"] == H for c in cams)
+
+
+def test_flat_gaussians_resize_keeps_base_and_alignment():
+    """The trainer's state buffers are allocated for a capacity and re-laid out in place when densify changes the
+    Gaussian count: the base address (what peers have mapped) stays, every segment starts on a 16-byte boundary for
+    every count, the layout equals the C side's gsb_flat_layout rule, and a count beyond the capacity is refused."""
+    import gsb200  # noqa: F401
+    from gsb200 import train
+    F = train.FlatGaussians(1000, "cpu", capacity=train.headroom(1000))
+    base = F.store.data_ptr()
+    assert F.capacity >= 1500 and F.flat.numel() == train.flat_layout(1000)[1]
+    for n in (1000, 1, 3, 1499, F.capacity):
+        F.resize(n)
+        offs, total = train.flat_layout(n)
+        assert F.n == n and F.flat.data_ptr() == base and F.flat.numel() == total
+        for k in train.KEYS:
+            v = F[k]
+            assert (v.data_ptr() - base) == 4 * offs[k] and (v.data_ptr() - base) % 16 == 0
+            assert v.numel() == n * train.WIDTH[k] and tuple(v.shape) == train.SHAPE[k](n)
+        assert total <= F.store.numel()
+    with pytest.raises(ValueError):
+        F.resize(F.capacity + 1)
+    # the layout rule of csrc/optimizer.cu gsb_flat_layout: widths 3, 3, 4, 1, 48, each segment padded to 4 floats
+    offs, total = train.flat_layout(5)
+    assert [offs[k] for k in train.KEYS] == [0, 16, 32, 52, 60] and total == 60 + 240

@@ -66,6 +66,18 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / steps * 1e6
 
+    # the resident trainer loop on the same box, same camera, for comparison
+    from gsb200 import train
+    T = train.Trainer([cam], targets=[target], params=params, config={"num_iterations": 7000, "lr_scheduler_config": {
+        "lr_pos": 1e-6, "lr_scale": 5e-7, "lr_rot": 5e-7, "lr_sh": 2e-7, "lr_opac": 5e-7, "final_lr_factor": 0.01}})
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(30):
+            T.train_step(it + 1, [0], densify=False)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 30 * 1e6
+    print(f"trainer (resident state, preallocated buffers)  {dt:8.1f} us/step")
     for h2d in ("none", "side", "main"):
         for rb in ("none", "async", "sync"):
             run(h2d, rb, 8)

@@ -103,7 +103,10 @@ GSB_API int gsb_create(gsb_ctx** out, int device) {
     return GSB_ERR_CUDA;
   }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->coop_launch = prop.cooperativeLaunch != 0;
+  }
   if (cudaMalloc((void**)&ctx->d_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_scalars, 16 * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->sort_small, (256 + 16) * sizeof(uint32_t)) != cudaSuccess ||
@@ -130,6 +133,7 @@ GSB_API int gsb_destroy(gsb_ctx* ctx) {
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->rank_base) cudaFree(ctx->rank_base);
+  if (ctx->sort_coop_state) cudaFree(ctx->sort_coop_state);
   if (ctx->bwd_acc) cudaFree(ctx->bwd_acc);
   if (ctx->bwd_acc_stage) cudaFree(ctx->bwd_acc_stage);
   if (ctx->ev_count) cudaEventDestroy(ctx->ev_count);
@@ -158,6 +162,10 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
   }
   if (!strcmp(name, "tile_sort") && value >= 0 && value <= 2) {
     ctx->opt.tile_sort = value;
+    return GSB_OK;
+  }
+  if (!strcmp(name, "sort_coop") && (value == 0 || value == 1)) {
+    ctx->opt.sort_coop = value;
     return GSB_OK;
   }
   if (!strcmp(name, "bwd_packed") && (value == 0 || value == 1)) {

@@ -24,13 +24,15 @@ struct gsb_ctx {
   char err[512] = {0};
   int64_t launches = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: done once per context, not per process
-  bool smem_optin_blend_bwd = false, smem_optin_radix = false, smem_optin_tilesort = false;
+  bool smem_optin_blend_bwd = false, smem_optin_radix = false, smem_optin_tilesort = false, smem_optin_radix_coop = false;
+  bool coop_launch = false;   // cudaDevAttrCooperativeLaunch
   // A/B knobs of gsb_set_option (per context; results never depend on them)
   struct Options {
     int binning = 0;     // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
     int blend_cull = 1;  // per-block culling masks in the tile kernels
     int tile_sort = 2;   // 0: bitonic network for every tile; 1: per-tile LSD radix sort (bitonic for tiles > 4096); 2 (default): radix when the longest list > 2048
     int bwd_reduce = 2;  // 2 (1 is accepted as a synonym): tensor-core pixel sums; 0: warp-shuffle butterfly with the exact exponential
+    int sort_coop = 1;   // 1: gsb_sort_pairs64 sorts inputs of up to num_sms x 12288 pairs in one cooperative launch; 0: three kernels per pass
     int bwd_packed = 1;  // 1: the tensor-core backward accumulates into packed records with vector REDs; 0: nine scalar REDs
   } opt;
 
@@ -44,6 +46,7 @@ struct gsb_ctx {
   uint32_t* sort_table = nullptr;
   int64_t sort_table_cap = 0;  // in uint32 entries
   uint32_t* sort_small = nullptr;  // [8*256] global digit bases + counters
+  uint32_t* sort_coop_state = nullptr;  // cooperative sort: grid-barrier counters + digit totals (zero between launches)
   // generic scan scratch
   int32_t* scan_sums = nullptr;
   int64_t scan_cap = 0;

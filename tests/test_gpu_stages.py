@@ -40,10 +40,13 @@ def test_prefix_sum(L, n):
     assert last.value == int(excl[-1])                                         # quirk G5: last flag not counted
 
 
+@pytest.mark.parametrize("coop", [1, 0])
 @pytest.mark.parametrize("n,bits,distinct", [(1, 44, 0), (77, 44, 0), (4096, 44, 0), (4097, 47, 0), (200000, 44, 0),
-                                              (200000, 44, 37), (1 << 20, 64, 0), (300001, 40, 2)])
-def test_radix_sort_pairs_is_stable(L, n, bits, distinct):
-    """Ascending, STABLE (ties keep their input order) -- forward.py:799-803 [Warp]."""
+                                              (200000, 44, 37), (1 << 20, 64, 0), (300001, 40, 2),
+                                              (2049, 24, 3), (12289, 33, 0), (148 * 12288, 44, 0), (148 * 12288 + 1, 41, 0)])
+def test_radix_sort_pairs_is_stable(L, n, bits, distinct, coop):
+    """Ascending, STABLE (ties keep their input order) -- forward.py:799-803 [Warp].  coop = 1: one cooperative
+    launch for all passes (inputs of up to num_sms x 12288 pairs); 0: three kernels per pass (any size)."""
     rng = np.random.default_rng(n + bits)
     if distinct:
         keys = rng.integers(0, distinct, n).astype(np.int64) << 20          # massive ties
@@ -54,7 +57,14 @@ def test_radix_sort_pairs_is_stable(L, n, bits, distinct):
     vals = np.arange(n, dtype=np.int32)
     ctx, s = L.context(), L.stream_ptr()
     dk, dv = _cuda(keys), _cuda(vals)
-    ctx.check(L.lib().gsb_sort_pairs64(ctx.h, s, L.ptr(dk), L.ptr(dv), None, None, n, 0, bits))
+    ctx.set_option("sort_coop", coop)
+    try:
+        for _ in range(2):   # twice: the cooperative kernel must leave its grid-barrier counters reusable
+            dk, dv = _cuda(keys), _cuda(vals)
+            ctx.check(L.lib().gsb_sort_pairs64(ctx.h, s, L.ptr(dk), L.ptr(dv), None, None, n, 0, bits))
+            torch.cuda.synchronize()
+    finally:
+        ctx.set_option("sort_coop", 1)
     order = np.argsort(keys, kind="stable")
     assert np.array_equal(dk.cpu().numpy(), keys[order])
     assert np.array_equal(dv.cpu().numpy(), vals[order])

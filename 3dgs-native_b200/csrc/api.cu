@@ -160,7 +160,7 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
     ctx->opt.blend_cull = value;
     return GSB_OK;
   }
-  if (!strcmp(name, "tile_sort") && value >= 0 && value <= 2) {
+  if (!strcmp(name, "tile_sort") && value >= 0 && value <= 3) {
     ctx->opt.tile_sort = value;
     return GSB_OK;
   }

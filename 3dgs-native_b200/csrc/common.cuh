@@ -30,7 +30,7 @@ struct gsb_ctx {
   struct Options {
     int binning = 0;     // 0: per-tile counting sort + shared-memory sort (default); 1: global 64-bit radix sort
     int blend_cull = 1;  // per-block culling masks in the tile kernels
-    int tile_sort = 2;   // 0: bitonic network for every tile; 1: per-tile LSD radix sort (bitonic for tiles > 4096); 2 (default): radix when the longest list > 2048
+    int tile_sort = 3;   // 3 (default): one-pass bucket sort by depth (bitonic for tiles > 4096); 0: bitonic network for every tile; 1: per-tile LSD radix sort (bitonic for tiles > 4096); 2: radix when the longest list > 2048
     int bwd_reduce = 2;  // 2 (1 is accepted as a synonym): tensor-core pixel sums; 0: warp-shuffle butterfly with the exact exponential
     int sort_coop = 1;   // 1: gsb_sort_pairs64 sorts inputs of up to num_sms x 12288 pairs in one cooperative launch; 0: three kernels per pass
     int bwd_packed = 1;  // 1: the tensor-core backward accumulates into packed records with vector REDs; 0: nine scalar REDs

@@ -319,6 +319,142 @@ tile_radix_kernel(const int2* __restrict__ ranges, const unsigned long long* __r
   for (int i = tid; i < count; i += 256) point_list[rg.x + i] = (int)ids[i];
 }
 
+
+// One CTA per tile: ONE-pass bucket sort of the segment's (depth_bits << 32 | id) composites (round 2, default).
+// The per-tile LSD radix sort above pays one VOTE per key bit and round of 32 keys (8 cycles per scheduler each,
+// tools/ubench/warp_ops.cu), the bitonic network log^2 n compare-exchanges; but the keys are depths -- floats spread
+// over the view's range -- so an order-preserving map  bucket = (depth_bits - min) >> shift  onto CAP >= n buckets
+// leaves about one entry per bucket:
+//   load      the entries into registers (CAP / 256 per thread), block minimum / maximum of the depth bits;
+//   count     one shared-memory atomic per entry;   scan: exclusive prefix over the buckets;
+//   scatter   one returning shared-memory atomic per entry (the order inside a bucket is arbitrary);
+//   finish    an entry's final position is the start of its bucket + the number of smaller 64-bit composites in the
+//             bucket (counted by the entry's own thread) -- the order of the reference's stable sort (tile | depth
+//             keys over an id-ordered list): ties of the depth bits come out by ascending id, whatever order the
+//             atomics arrived in.
+// Degenerate segments (one bucket with more than kBucketLimit entries: many equal or nearly equal depths) fall back
+// to the bitonic network inside the same CTA.  Tiles whose count is outside (lo, hi] return at once.
+constexpr int kBucketLimit = 32;
+
+// The sort of one segment of 2 <= count <= CAP entries with CAP buckets (CAP / 256 entries and buckets per thread).
+template <int CAP>
+__device__ __forceinline__ void tile_bucket_segment(const int2 rg, const unsigned long long* __restrict__ binned,
+                                                    int* __restrict__ point_list, unsigned long long* s_dst,
+                                                    unsigned* s_min, unsigned* s_max, unsigned* s_wtot) {
+  constexpr int E = CAP / 256;   // entries per thread, buckets per thread
+  constexpr int LOG_CAP = CAP == 1024 ? 10 : CAP == 2048 ? 11 : 12;
+  static_assert(CAP == (1 << LOG_CAP), "CAP must be 1024, 2048 or 4096");
+  unsigned* const cursor = reinterpret_cast<unsigned*>(s_dst + CAP);  // [CAP] bucket counts -> starts -> ends
+  const int count = rg.y - rg.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long e[E];
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const int i = tid + 256 * j;
+    e[j] = i < count ? binned[rg.x + i] : ~0ull;
+    if (i < count) {
+      const unsigned k = (unsigned)(e[j] >> 32);
+      kmin = min(kmin, k);
+      kmax = max(kmax, k);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < E / 4; ++j) reinterpret_cast<uint4*>(cursor)[tid + 256 * j] = make_uint4(0u, 0u, 0u, 0u);
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) s_min[warp] = kmin, s_max[warp] = kmax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) kmin = min(kmin, s_min[w]), kmax = max(kmax, s_max[w]);
+  const unsigned range = kmax - kmin;
+  const int sh = max(0, (32 - __clz(range)) - LOG_CAP);   // (range >> sh) < CAP
+#pragma unroll
+  for (int j = 0; j < E; ++j)
+    if (tid + 256 * j < count) atomicAdd(&cursor[((unsigned)(e[j] >> 32) - kmin) >> sh], 1u);
+  __syncthreads();
+  // exclusive scan over the buckets; thread t owns buckets t E .. t E + E - 1
+  unsigned c[E], sum = 0u, cmax = 0u;
+#pragma unroll
+  for (int j = 0; j < E / 4; ++j) {
+    const uint4 v = reinterpret_cast<const uint4*>(cursor)[tid * (E / 4) + j];
+    c[4 * j + 0] = v.x, c[4 * j + 1] = v.y, c[4 * j + 2] = v.z, c[4 * j + 3] = v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    cmax = max(cmax, c[j]);
+    const unsigned t = c[j];
+    c[j] = sum;
+    sum += t;
+  }
+  unsigned inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wtot[warp] = inc;
+  if (__syncthreads_or(cmax > (unsigned)kBucketLimit)) {   // (also orders s_wtot and the reads of cursor)
+    tile_sort_segment(rg, binned, point_list, s_dst);      // degenerate depths: the bitonic network (n_pad <= CAP)
+    return;                                                // (uniform: the whole CTA takes this path)
+  }
+  unsigned base = inc - sum;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (w < warp) base += s_wtot[w];
+#pragma unroll
+  for (int j = 0; j < E / 4; ++j)
+    reinterpret_cast<uint4*>(cursor)[tid * (E / 4) + j] =
+        make_uint4(base + c[4 * j], base + c[4 * j + 1], base + c[4 * j + 2], base + c[4 * j + 3]);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < E; ++j)
+    if (tid + 256 * j < count) {
+      const unsigned pos = atomicAdd(&cursor[((unsigned)(e[j] >> 32) - kmin) >> sh], 1u);
+      GSB_DCHECK(pos < (unsigned)count);
+      s_dst[pos] = e[j];
+    }
+  __syncthreads();
+  // cursor[b] is now the END of bucket b.  Every entry finds its final place by itself: the start of its bucket plus
+  // the number of entries of the bucket below it (composites are unique: the id is part of them).  One thread per
+  // ENTRY, no dependent chain -- the first version let thread t insertion-sort the slice of its buckets, and the
+  // CTA waited a third of the kernel's time for the thread with the longest slice (ncu: 31% of the samples at the
+  // barrier behind it).
+#pragma unroll
+  for (int j = 0; j < E; ++j)
+    if (tid + 256 * j < count) {
+      const unsigned b = ((unsigned)(e[j] >> 32) - kmin) >> sh;
+      const int s0 = b == 0u ? 0 : (int)cursor[b - 1], s1 = (int)cursor[b];
+      int r = 0;
+      for (int i = s0; i < s1; ++i) r += (s_dst[i] < e[j]) ? 1 : 0;
+      GSB_DCHECK(s0 + r < count);
+      point_list[rg.x + s0 + r] = (int)(unsigned)e[j];
+    }
+}
+
+// MAXCAP sizes the launch's shared memory (12 bytes per entry); each tile runs the instance that fits its count, so
+// a frame whose longest list is 1100 entries still sorts its 600-entry tiles with 1024 buckets and 4 entries per thread.
+template <int MAXCAP>
+__global__ void __launch_bounds__(256)
+tile_bucket_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
+                   int* __restrict__ point_list, int lo, int hi) {
+  extern __shared__ __align__(16) unsigned long long s_dst[];      // [CAP] entries in bucket order + [CAP] cursors
+  __shared__ unsigned s_min[8], s_max[8], s_wtot[8];
+  const int2 rg = ranges[blockIdx.x];
+  const int count = rg.y - rg.x;
+  if (count <= lo || count > hi) return;
+  if (count == 1) {
+    if (threadIdx.x == 0) point_list[rg.x] = (int)(unsigned)binned[rg.x];
+    return;
+  }
+  if (MAXCAP == 1024 || count <= 1024)
+    tile_bucket_segment<1024>(rg, binned, point_list, s_dst, s_min, s_max, s_wtot);
+  else if (MAXCAP == 2048 || count <= 2048)
+    tile_bucket_segment<(MAXCAP >= 2048 ? 2048 : 1024)>(rg, binned, point_list, s_dst, s_min, s_max, s_wtot);
+  else
+    tile_bucket_segment<MAXCAP>(rg, binned, point_list, s_dst, s_min, s_max, s_wtot);
+}
+
 }  // namespace
 
 
@@ -411,9 +547,23 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                                        kMaxTileSort * 8));
     GSB_CUDA(ctx, cudaFuncSetAttribute(tile_radix_kernel<kRadixCap>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)radix_smem(kRadixCap)));
+    GSB_CUDA(ctx, cudaFuncSetAttribute(tile_bucket_kernel<kRadixCap>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kRadixCap * 12));
     attr_set = true;
   }
   int bitonic_lo = 0;  // the bitonic kernel sorts tiles with more than this many entries
+  if (ctx->opt.tile_sort == 3) {
+    // one-pass bucket sort for tiles of up to 4096 entries (12 bytes of shared memory per entry of the capacity)
+    if (max_count <= 1024) {
+      GSB_LAUNCH(ctx, tile_bucket_kernel<1024>, num_tiles, 256, 1024 * 12, s, rg, binned, point_list, 0, 1024);
+    } else if (max_count <= 2048) {
+      GSB_LAUNCH(ctx, tile_bucket_kernel<2048>, num_tiles, 256, 2048 * 12, s, rg, binned, point_list, 0, 2048);
+    } else {
+      GSB_LAUNCH(ctx, tile_bucket_kernel<kRadixCap>, num_tiles, 256, kRadixCap * 12, s, rg, binned, point_list, 0, kRadixCap);
+    }
+    if (max_count <= kRadixCap) return GSB_OK;
+    bitonic_lo = kRadixCap;
+  }
   if (ctx->opt.tile_sort == 1 || (ctx->opt.tile_sort == 2 && max_count > 2048)) {
     if (max_count <= 1024) {
       GSB_LAUNCH(ctx, tile_radix_kernel<1024>, num_tiles, 256, radix_smem(1024), s, rg, binned, point_list, 0, 1024);

@@ -65,8 +65,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--cull", type=int, default=1)
-    ap.add_argument("--tile-sort", type=int, default=2,
-                    help="A/B: 0 bitonic per tile, 1 per-tile radix sort, 2 (default) radix when the longest list > 2048")
+    ap.add_argument("--tile-sort", type=int, default=3,
+                    help="A/B: 3 (default) one-pass bucket sort by depth, 0 bitonic per tile, 1 per-tile radix sort, "
+                         "2 radix when the longest list > 2048")
     ap.add_argument("--bwd-reduce", type=int, default=2, help="A/B: 0 shuffle butterfly, 1 / 2 tensor-core moments")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem", "hybrid"])
     ap.add_argument("--bwd-packed", type=int, default=1,

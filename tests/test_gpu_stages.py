@@ -120,16 +120,16 @@ def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax):
         oracle.set_threads(1)
     longest = int(np.diff(ob["ranges"], axis=1).max())
     ctx = L.context()
-    # (binning, tile_sort): bitonic per tile, per-tile radix sort (bitonic for tiles > 4096), the default choice
-    # between the two by list length, global radix sort
-    for mode, tile_sort in ((0, 0), (0, 1), (0, 2), (1, 2)):
+    # (binning, tile_sort): bitonic per tile, per-tile radix sort (bitonic for tiles > 4096), the choice between the
+    # two by list length, the one-pass bucket sort by depth (default), global radix sort
+    for mode, tile_sort in ((0, 0), (0, 1), (0, 2), (0, 3), (1, 2)):
         ctx.set_option("binning", mode)
         ctx.set_option("tile_sort", tile_sort)
         try:
             img, _, buf = forward.render_gaussians(**kw)
         finally:
             ctx.set_option("binning", 0)
-            ctx.set_option("tile_sort", 2)
+            ctx.set_option("tile_sort", 3)
         for k in ("point_offsets", "point_list", "ranges", "n_contrib", "radii"):
             assert np.array_equal(buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]), (mode, tile_sort, k, longest)
         assert np.abs(img.cpu().numpy() - o_img).max() <= 1e-4

@@ -41,10 +41,10 @@ def main():
 
     n, w, h = 3000, 96, 64
     params, cam, target = scene.synthetic_scene(n, w, h, 0.02, 0.12, seed=11)
-    for tile_sort in (0, 1):
+    for tile_sort in (0, 1, 3):
         ctx.set_option("tile_sort", tile_sort)
         img, depth, buf = forward.render_gaussians(**scene.render_kwargs(params, cam))
-    ctx.set_option("tile_sort", 2)
+    ctx.set_option("tile_sort", 3)
     ref = None
     for _ in range(3):                     # self-resetting scratch: same bits every time
         i2, d2, b2 = forward.render_gaussians(**scene.render_kwargs(params, cam))

@@ -10,15 +10,13 @@
 int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* v0, int64_t* k1, int32_t* v1,
                             int32_t* final_vals, int64_t n, int begin_bit, int end_bit, bool* result_in_second);
 int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                           const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
-                           int64_t* num_rendered_host, int* max_count_host);
+                           const int32_t* radii, int32_t* ranges, int64_t* num_rendered_host, int* max_count_host);
 int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles);
 int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges);
 int gsb_tile_binning_wait(gsb_ctx* ctx, int64_t* num_rendered_host, int* max_count_host);
 int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                          const float* depths, const int32_t* radii, const int32_t* rank_index,
-                          int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
-                          int32_t* point_list);
+                          const float* depths, const int32_t* radii, const int32_t* ranges, int64_t num_rendered,
+                          int max_count, int32_t* point_list);
 int gsb_tile_binning_max();
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
@@ -196,14 +194,8 @@ GSB_API int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s_, int32_t width, int32_t 
   int rc;
   int64_t D = 0;
   int max_count = 0;
-  rc = gsb_tile_binning_count(ctx, s, n, width, height, points_xy, radii, point_offsets, ranges, &D, &max_count);
+  rc = gsb_tile_binning_count(ctx, s, n, width, height, points_xy, radii, ranges, &D, &max_count);
   if (rc != GSB_OK) return rc;
-  if (D > ctx->bin_cap && D <= GSB_MAX_RENDERED) {
-    // first frame / scene grew: the rank buffer was too small.  Grow and redo the counting pass.
-    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
-    rc = gsb_tile_binning_count(ctx, s, n, width, height, points_xy, radii, point_offsets, ranges, &D, &max_count);
-    if (rc != GSB_OK) return rc;
-  }
   if (num_rendered_host) *num_rendered_host = D;
   if (used_tile_path_host) *used_tile_path_host = 0;
   if (D > (1LL << 30))  // forward.py:765-767
@@ -217,8 +209,8 @@ GSB_API int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s_, int32_t width, int32_t 
   if (D == 0) return GSB_OK;  // ranges are all (0,0) already
   if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
     // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
-    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, point_offsets, 0, ranges, D,
-                               max_count, point_list);
+    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, ranges, D, max_count, point_list);
     if (rc != GSB_OK) return rc;
     if (used_tile_path_host) *used_tile_path_host = 1;
   } else {
@@ -260,9 +252,9 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   // read-back so that it runs while the host wakes up and launches the rest.
   int64_t D = 0;
   int max_count = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  {
     if ((rc = gsb_tile_binning_prepare(ctx, s, n, num_tiles)) != GSB_OK) return rc;
-    PreBin bin{ctx->tile_count, ctx->vals_a, ctx->rank_base, ctx->d_scalars + 8, (long long)ctx->bin_cap};
+    PreBin bin{ctx->tile_count};
     rc = gsb_preprocess_impl(ctx, s, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds,
                              rgb, conic_opacity, ctx->tiles_touched, clamped_state, &bin);
     if (rc != GSB_OK) return rc;
@@ -272,9 +264,6 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
     // measured 4-7 us per step, the three scan kernels are not always hidden behind the host's wake-up)
     if (point_offsets && (rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK) return rc;
     if ((rc = gsb_tile_binning_wait(ctx, &D, &max_count)) != GSB_OK) return rc;
-    if (D <= ctx->bin_cap || D > GSB_MAX_RENDERED) break;
-    // first frame / scene grew: the rank buffer was too small.  Grow it and redo the pass.
-    if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
   }
   if (num_rendered_host) *num_rendered_host = D;
   if (D > (1LL << 30))  // forward.py:765-767
@@ -287,8 +276,10 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   if (D > 0) {
     if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
       // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
-      rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ctx->rank_base, 1, ranges, D,
-                                 max_count, point_list);
+      // (first frame / the scene grew: the segment buffer grows here, behind the read-back of D)
+      if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
+      rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ranges, D, max_count,
+                                 point_list);
       if (rc != GSB_OK) return rc;
     } else {
       // a tile list too long for the shared-memory sort (or the A/B switch): the reference's own

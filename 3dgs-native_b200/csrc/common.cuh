@@ -330,14 +330,9 @@ struct FrameK {
 struct FrameK;
 void gsb_make_framek(const gsb_frame* f, FrameK* k);
 
-// Counting pass of the tile binning fused into preprocess (gsb_forward only): per-tile counters, the
-// arrival ranks, each Gaussian's first rank index and the cursor those indices are drawn from.
+// Counting pass of the tile binning fused into preprocess (gsb_forward only): the per-tile counters.
 struct PreBin {
   int32_t* tile_count;
-  int32_t* rank;
-  int32_t* rank_base;
-  int32_t* cursor;
-  long long capacity;  // entries of `rank`
 };
 int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
                         const float* scales, const float* rotations, const float* opacities, const float* shs,

@@ -30,8 +30,6 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
                   float* __restrict__ cov3Ds, float* __restrict__ rgb, float4* __restrict__ conic_opacity,
                   int* __restrict__ tiles_touched, float* __restrict__ clamped_state, const PreBin bin) {
   __shared__ float s_sh[kPreThreads * kShStride];
-  __shared__ int s_wsum[kPreThreads / 32];
-  __shared__ int s_cta_base;
   const int base = blockIdx.x * kPreThreads;
   const int tid = threadIdx.x;
   const int rows = min(kPreThreads, n - base);
@@ -70,7 +68,7 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     }
   }
   __syncthreads();
-  if (!BIN && !live) return;
+  if (!live) return;
 
   // outputs default to zero: forward.py:703-710 allocates them with wp.zeros
   int o_radius = 0, o_tiles = 0;
@@ -222,48 +220,13 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     o_tiles = (rmaxy - rminy) * (rmaxx - rminx);
   } while (false);
 
-  if (BIN) {
-    // exclusive scan of o_tiles over the CTA, one cursor atomic per CTA
-    const int lane = tid & 31, warp = tid >> 5;
-    int incl = o_tiles;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    int wbase = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kPreThreads / 32; ++w) {
-      const int t = s_wsum[w];
-      if (w < warp) wbase += t;
-      total += t;
-    }
-    if (tid == 0) s_cta_base = (total > 0) ? atomicAdd(bin.cursor, total) : 0;
-    __syncthreads();
-    if (!live) return;
-    long long e = (long long)s_cta_base + wbase + incl - o_tiles;
-    bin.rank_base[i] = (int)e;
-    if (o_tiles > 0) {
-      // returning atomics in groups of four: four counters in flight per thread instead of one
-      const int w = rmaxx - rminx;
-      for (int t0 = 0; t0 < o_tiles; t0 += 4) {
-        int k[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u;
-          if (t < o_tiles) {
-            const int ty = t / w, tx = t - ty * w;
-            k[u] = atomicAdd(bin.tile_count + (size_t)((rminy + ty) * f.grid_x + rminx + tx) * kCntStride, 1);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (t0 + u < o_tiles && e + u < bin.capacity) bin.rank[e + u] = k[u];
-        e += 4;
-      }
-    }
+  if (BIN && o_tiles > 0) {
+    // counting pass of the tile binning: one RED per (Gaussian, tile) on the tile's counter.  (Round 1 drew the
+    // duplicate's arrival rank from a RETURNING atomic here and stored it for the scatter pass -- 16 us on top of
+    // the 23 us of the kernel, a block-wide scan for the rank slots and 4 B written + read per duplicate; now the
+    // scatter pass takes its slot from the counter itself, counting it back down to zero.)
+    for (int ty = rminy; ty < rmaxy; ++ty)
+      for (int tx = rminx; tx < rmaxx; ++tx) atomicAdd(bin.tile_count + (size_t)(ty * f.grid_x + tx) * kCntStride, 1);
   }
 
   radii[i] = o_radius;

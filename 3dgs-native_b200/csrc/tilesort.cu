@@ -5,12 +5,13 @@
 // The 64-bit key is (tile_id << 32) | depth_bits and the unsorted list is in ascending Gaussian
 // order, so the reference's stable sort orders the duplicates by (tile, depth_bits, gaussian_id).
 // Here the most significant digit -- the tile id -- is resolved by a counting sort:
-//   tile_count_kernel   one returning atomic per (Gaussian, tile) on a per-tile counter (one 128-byte
-//                       line per counter: neighbouring tiles must not serialise on one L2 line);
-//                       the returned arrival rank is stored at the duplicate's deterministic index
+//   tile_count_kernel   one RED per (Gaussian, tile) on a per-tile counter (one 128-byte line per counter:
+//                       neighbouring tiles must not serialise on one L2 line); inside gsb_forward this pass is
+//                       part of preprocess_kernel
 //   tile_scan_kernel    exclusive scan of the counts = the tile ranges (and D, and the max count)
-//   tile_scatter_kernel every duplicate goes to slot start[tile] + rank as (depth_bits<<32 | id);
-//                       no atomics: the rank was recorded by the counting pass
+//   tile_scatter_kernel every duplicate takes a slot of its tile's segment by counting the tile's counter back
+//                       DOWN (one returning atomic; the order inside the segment is arbitrary, the sort fixes it)
+//                       and goes there as (depth_bits<<32 | id); the counters end the frame at zero
 //   tile_sort_kernel    one CTA per tile sorts its segment (bitonic network on the 64-bit
 //                       composites -- they are unique, so any correct sort gives the stable order;
 //                       strides below 64 run in registers with shuffles, only the wide strides go
@@ -27,9 +28,8 @@ namespace {
 constexpr int kCntStride = 32;  // ints between two tiles' counters = one 128-byte line each
 
 __global__ void __launch_bounds__(256)
-tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ radii,
-                  const int* __restrict__ point_offsets, int grid_x, int grid_y, int64_t capacity,
-                  int* __restrict__ tile_count, int* __restrict__ rank) {
+tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ radii, int grid_x, int grid_y,
+                  int* __restrict__ tile_count) {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n) return;
   int r = radii[tid];
@@ -37,22 +37,17 @@ tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ 
   float2 p = xy[tid];
   int rminx, rminy, rmaxx, rmaxy;
   gs_get_rect(p.x, p.y, (float)r, (float)grid_x, (float)grid_y, rminx, rminy, rmaxx, rmaxy);
-  int64_t e = (tid > 0) ? point_offsets[tid - 1] : 0;  // index of this Gaussian's first duplicate
   for (int y = rminy; y < rmaxy; ++y)
-    for (int x = rminx; x < rmaxx; ++x) {
-      const int k = atomicAdd(tile_count + (size_t)(y * grid_x + x) * kCntStride, 1);
-      if (e < capacity) rank[e] = k;
-      ++e;
-    }
+    for (int x = rminx; x < rmaxx; ++x) atomicAdd(tile_count + (size_t)(y * grid_x + x) * kCntStride, 1);
 }
 
 // Single CTA: exclusive scan over the tiles.  Writes ranges (start,end) -- (0,0) for empty tiles,
 // like the zero-initialised reference buffer --, the per-tile write cursors, the total and the max.
-// It is the last reader of the counters and of the rank cursor, so it leaves both zeroed for the next
-// frame (gsb_tile_binning_prepare then skips its two memsets).
+// The counters keep their counts: the scatter pass takes its slots from them and leaves them at zero for the next
+// frame (gsb_tile_binning_prepare then skips its memset).
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__ ranges,
-                 int* __restrict__ out_total_max, int* __restrict__ cursor) {
+tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __restrict__ ranges,
+                 int* __restrict__ out_total_max) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_max[32];
@@ -71,7 +66,6 @@ tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__
     int local = 0;
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-      if (c[k] != 0) tile_count[(size_t)(i0 + k) * kCntStride] = 0;
       my_max = max(my_max, c[k]);
       local += c[k];
     }
@@ -108,21 +102,19 @@ tile_scan_kernel(int num_tiles, int* __restrict__ tile_count, int2* __restrict__
     for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
     out_total_max[0] = s_carry;
     out_total_max[1] = m;
-    *cursor = 0;
   }
 }
 
 // LANES threads per Gaussian: lane t of the group writes the tiles t, t + LANES, ... of the Gaussian's rectangle.
-// With eight lanes the ranks are read in 32-byte pieces and a Gaussian that covers a hundred tiles (6M Gaussians at
-// 4K: 18 per visible Gaussian, with a long tail) no longer makes one thread walk them all while its warp waits: 0.83
-// against 1.05 ms at that size (68 M duplicates).  At the headline size (5.7 tiles per visible Gaussian) the seven
-// extra lanes mostly idle and one thread per Gaussian is faster (15 against 23 us): the host picks by D / n.
+// With eight lanes a Gaussian that covers a hundred tiles (6M Gaussians at 4K: 18 per visible Gaussian, with a long
+// tail) no longer makes one thread walk them all while its warp waits.  At the headline size (5.7 tiles per visible
+// Gaussian) the seven extra lanes mostly idle and one thread per Gaussian is faster: the host picks by D / n.
+// The slot inside the tile's segment is the tile's counter, counted down: up to four returning atomics in flight.
 template <int kScatterLanes>
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
-                    const int* __restrict__ radii, const int* __restrict__ rank_index, int index_is_exclusive,
-                    int grid_x, int grid_y, const int2* __restrict__ ranges, const int* __restrict__ rank,
-                    unsigned long long* __restrict__ binned) {
+                    const int* __restrict__ radii, int grid_x, int grid_y, const int2* __restrict__ ranges,
+                    int* __restrict__ tile_count, unsigned long long* __restrict__ binned) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int gid = (int)(t / kScatterLanes), sub = (int)(t % kScatterLanes);
   if (gid >= n) return;
@@ -132,20 +124,32 @@ tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restric
   int rminx, rminy, rmaxx, rmaxy;
   gs_get_rect(p.x, p.y, (float)r, (float)grid_x, (float)grid_y, rminx, rminy, rmaxx, rmaxy);
   const unsigned long long v = ((unsigned long long)__float_as_uint(depths[gid]) << 32) | (unsigned)gid;
-  // first rank of this Gaussian: rank_base[gid] (fused counting pass) or the inclusive scan shifted by one
-  const int64_t e = index_is_exclusive ? rank_index[gid] : ((gid > 0) ? rank_index[gid - 1] : 0);
   const int w = rmaxx - rminx, cnt = w * (rmaxy - rminy);
   if (w <= 0) return;
-  int y = rminy + sub / w, x = rminx + sub % w;   // tile `sub` of the rectangle, row-major like the counting pass
-  for (int k = sub; k < cnt; k += kScatterLanes) {
-    GSB_DCHECK(y < rmaxy && x >= rminx && x < rmaxx);
-    GSB_DCHECK(rank[e + k] >= 0 && rank[e + k] < ranges[y * grid_x + x].y - ranges[y * grid_x + x].x);
-    binned[ranges[y * grid_x + x].x + rank[e + k]] = v;
-    x += kScatterLanes;
-    while (x >= rmaxx) {
-      x -= w;
-      ++y;
+  int y = rminy + sub / w, x = rminx + sub % w;   // tile `sub` of the rectangle, row-major
+  for (int k = sub; k < cnt; k += 4 * kScatterLanes) {
+    int tile[4], slot[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      tile[u] = -1;
+      if (k + u * kScatterLanes < cnt) {
+        GSB_DCHECK(y < rmaxy && x >= rminx && x < rmaxx);
+        tile[u] = y * grid_x + x;
+        slot[u] = atomicSub(tile_count + (size_t)tile[u] * kCntStride, 1) - 1;
+        x += kScatterLanes;
+        while (x >= rmaxx) {
+          x -= w;
+          ++y;
+        }
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (tile[u] >= 0) {
+        const int2 rg = ranges[tile[u]];
+        GSB_DCHECK(slot[u] >= 0 && slot[u] < rg.y - rg.x);
+        binned[rg.x + slot[u]] = v;
+      }
   }
 }
 
@@ -459,30 +463,24 @@ tile_bucket_kernel(const int2* __restrict__ ranges, const unsigned long long* __
 
 
 // ---- host side -------------------------------------------------------------------------------
-// prepare: size and zero the per-tile counters (and the rank cursor of the fused counting pass)
+// prepare: size and zero the per-tile counters
 int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles) {
+  (void)n;
   const int64_t need = (int64_t)num_tiles * kCntStride, old_cap = ctx->tile_cap;
   int rc = gsb_grow(ctx, (void**)&ctx->tile_count, &ctx->tile_cap, need, sizeof(int32_t), s);
   if (rc != GSB_OK) return rc;
   if (ctx->tile_cap != old_cap) ctx->tile_clean = 0;  // reallocated: contents unknown
-  // The arrival ranks live in vals_a (one int per duplicate).  Its capacity is a guess until D is
-  // known (previous frame's D); if it turns out too small the caller re-runs the counting pass.
-  if (ctx->bin_cap == 0 && (rc = gsb_reserve_binning(ctx, s, 4 * (int64_t)n + 1024)) != GSB_OK) return rc;
-  // The previous frame's tile_scan_kernel left the counters and the cursor zeroed (tile_clean); only the
-  // first frame, a larger tile grid, or a frame that failed between here and its scan pays the memsets.
-  if (ctx->tile_clean < need) {
-    GSB_CUDA(ctx, cudaMemsetAsync(ctx->tile_count, 0, sizeof(int32_t) * (size_t)need, s));
-    GSB_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars + 8, 0, sizeof(int32_t), s));
-  }
-  ctx->tile_clean = 0;  // dirty from here until the scan has been queued
+  // The previous frame's scatter pass counted every counter back to zero (tile_clean); only the first frame, a
+  // larger tile grid, or a frame that did not reach its scatter pass (an error, the global-sort path) pays the memset.
+  if (ctx->tile_clean < need) GSB_CUDA(ctx, cudaMemsetAsync(ctx->tile_count, 0, sizeof(int32_t) * (size_t)need, s));
+  ctx->tile_clean = 0;  // dirty from here until the scatter pass has been queued
   return GSB_OK;
 }
 
 // scan the counters into ranges, start the read-back of (D, max count) and mark it with an event
 int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges) {
   GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
-             ctx->d_scalars + 4, ctx->d_scalars + 8);
-  ctx->tile_clean = (int64_t)num_tiles * kCntStride;
+             ctx->d_scalars + 4);
   GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
   return GSB_OK;
@@ -499,38 +497,34 @@ int gsb_tile_binning_wait(gsb_ctx* ctx, int64_t* num_rendered_host, int* max_cou
 
 // Stand-alone counting pass (gsb_bin_by_tile): on return *num_rendered_host and *max_count_host are set.
 int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                           const int32_t* radii, const int32_t* point_offsets, int32_t* ranges,
-                           int64_t* num_rendered_host, int* max_count_host) {
+                           const int32_t* radii, int32_t* ranges, int64_t* num_rendered_host, int* max_count_host) {
   const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
   const int num_tiles = gx * gy;
   int rc = gsb_tile_binning_prepare(ctx, s, n, num_tiles);
   if (rc != GSB_OK) return rc;
   if (n > 0)
     GSB_LAUNCH(ctx, tile_count_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
-               radii, point_offsets, gx, gy, ctx->bin_cap, ctx->tile_count, ctx->vals_a);
+               radii, gx, gy, ctx->tile_count);
   if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges)) != GSB_OK) return rc;
   return gsb_tile_binning_wait(ctx, num_rendered_host, max_count_host);
 }
 
-// rank_index: point_offsets (index_is_exclusive = 0) or the fused pass's rank_base (= 1)
+// precondition (checked by the caller): ctx->bin_cap >= num_rendered and the counters hold this frame's counts
 int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
-                          const float* depths, const int32_t* radii, const int32_t* rank_index,
-                          int index_is_exclusive, const int32_t* ranges, int64_t num_rendered, int max_count,
-                          int32_t* point_list) {
+                          const float* depths, const int32_t* radii, const int32_t* ranges, int64_t num_rendered,
+                          int max_count, int32_t* point_list) {
   const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
   const int num_tiles = gx * gy;
-  // precondition (checked by the caller): ctx->bin_cap >= num_rendered, so every rank was recorded
   unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
   const int2* rg = reinterpret_cast<const int2*>(ranges);
   if (num_rendered > 8 * (int64_t)n) {
     GSB_LAUNCH(ctx, tile_scatter_kernel<8>, (unsigned)gsb_div_up((int64_t)n * 8, 256), 256, 0, s, n,
-               reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
-               ctx->vals_a, binned);
+               reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned);
   } else {
     GSB_LAUNCH(ctx, tile_scatter_kernel<1>, (unsigned)gsb_div_up(n, 256), 256, 0, s, n,
-               reinterpret_cast<const float2*>(points_xy), depths, radii, rank_index, index_is_exclusive, gx, gy, rg,
-               ctx->vals_a, binned);
+               reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned);
   }
+  ctx->tile_clean = (int64_t)num_tiles * kCntStride;   // every counter is back at zero when the scatter pass has run
   // Per-tile sort: the bitonic network (O(n log^2 n), pure register / shuffle / shared-memory compare-exchange) or
   // the O(n) shared-memory LSD radix sort for tiles of up to 4096 entries (longer ones always go to the bitonic
   // kernel; each kernel skips the other's tiles).  Measured on a B200, whole forward, L2 flushed:

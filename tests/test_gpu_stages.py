@@ -100,25 +100,41 @@ def test_duplicate_keys_and_ranges_vs_oracle(L, oracle):
     assert np.array_equal(ranges.cpu().numpy(), ob["ranges"])
 
 
-@pytest.mark.parametrize("n,w,h,smin,smax", [(20000, 320, 240, 0.005, 0.05),   # short lists  (<= 1024 per tile)
-                                              (6000, 64, 48, 0.1, 0.4),         # long lists   (> 1024 per tile)
-                                              (9000, 32, 32, 0.5, 1.5),         # every Gaussian in every tile (> 4096)
-                                              (14000, 96, 64, 0.02, 0.6),       # mixed: some tiles below, some above 4096
-                                              (18000, 16, 16, 1.0, 2.0)])       # one tile, > 16384 entries: radix fallback
-def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax):
+@pytest.mark.parametrize("n,w,h,smin,smax,heavy", [
+    (20000, 320, 240, 0.005, 0.05, 0),   # short lists  (<= 1024 per tile)
+    (6000, 64, 48, 0.1, 0.4, 0),         # long lists   (> 1024 per tile)
+    (9000, 32, 32, 0.5, 1.5, 0),         # every Gaussian in every tile (> 4096)
+    (14000, 96, 64, 0.02, 0.6, 0),       # mixed: some tiles below, some above 4096
+    (18000, 16, 16, 1.0, 2.0, 0),        # one tile, > 16384 entries: radix fallback
+    (6000, 64, 48, 0.1, 0.4, 1),         # a third of the Gaussians at ONE position: hundreds of equal depths per tile
+    (3000, 160, 96, 0.02, 0.2, 2)])      # all depths within a few ulp of each other (one plane facing the camera)
+def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax, heavy):
     """gsb_forward's per-tile counting sort + shared-memory sort and the global radix sort give the
-    same point_list / ranges / n_contrib as the oracle's stable sort (incl. exact depth ties)."""
+    same point_list / ranges / n_contrib as the oracle's stable sort (incl. exact depth ties; the degenerate depth
+    distributions send the one-pass bucket sort to its bitonic fallback)."""
     import gsb200  # noqa: F401
     from gsb200 import forward
     kw = _scene(n, w, h, smin, smax, n)
     kw["means3D"] = kw["means3D"].copy()
     kw["means3D"][1::7] = kw["means3D"][0::7][: len(kw["means3D"][1::7])]     # duplicates => depth ties
+    if heavy == 1:
+        kw["means3D"][::3] = kw["means3D"][0]
+    elif heavy == 2:
+        # move every centre onto the plane through the first one, perpendicular to the viewing direction
+        view = np.asarray(kw["viewmatrix"], dtype=np.float64).reshape(4, 4)
+        fwd = view[:3, 2]                     # depth = (p, 1) . view[:, 2]  (row vector times matrix, forward.py:246)
+        m = kw["means3D"].astype(np.float64)
+        m -= np.outer((m - m[0]) @ fwd, fwd)
+        kw["means3D"] = m.astype(np.float32)
     oracle.set_threads(oracle.max_threads())
     try:
         o_img, _, ob = oracle.render_gaussians(**kw)
     finally:
         oracle.set_threads(1)
     longest = int(np.diff(ob["ranges"], axis=1).max())
+    if heavy == 2:
+        vis = ob["radii"].reshape(-1) > 0
+        assert vis.sum() > 100 and np.ptp(ob["depths"].reshape(-1)[vis]) <= 1e-5 * ob["depths"].reshape(-1)[vis].mean()
     ctx = L.context()
     # (binning, tile_sort): bitonic per tile, per-tile radix sort (bitonic for tiles > 4096), the choice between the
     # two by list length, the one-pass bucket sort by depth (default), global radix sort

@@ -12,11 +12,15 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
 int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
                            const int32_t* radii, int32_t* ranges, int64_t* num_rendered_host, int* max_count_host);
 int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles);
-int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges);
+int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges, int spec_cap, int spec_max);
+int gsb_blend_forward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
+                           const int32_t* point_list, const float* points_xy, const float* rgb,
+                           const float* conic_opacity, const float* depths, float* image, float* inv_depth,
+                           float* final_T, int32_t* n_contrib, int32_t* block_masks, const int* go);
 int gsb_tile_binning_wait(gsb_ctx* ctx, int64_t* num_rendered_host, int* max_count_host);
 int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
                           const float* depths, const int32_t* radii, const int32_t* ranges, int64_t num_rendered,
-                          int max_count, int32_t* point_list);
+                          int max_count, int32_t* point_list, const int* go);
 int gsb_tile_binning_max();
 
 int gsb_set_error(gsb_ctx* ctx, int code, const char* fmt, ...) {
@@ -162,6 +166,10 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
     ctx->opt.tile_sort = value;
     return GSB_OK;
   }
+  if (!strcmp(name, "speculate") && (value == 0 || value == 1)) {
+    ctx->opt.speculate = value;
+    return GSB_OK;
+  }
   if (!strcmp(name, "sort_coop") && (value == 0 || value == 1)) {
     ctx->opt.sort_coop = value;
     return GSB_OK;
@@ -210,7 +218,8 @@ GSB_API int gsb_bin_by_tile(gsb_ctx* ctx, gsb_stream s_, int32_t width, int32_t 
   if (ctx->opt.binning == 0 && max_count <= gsb_tile_binning_max()) {
     // duplicate + sort + ranges (forward.py:776-840) as counting sort by tile + per-tile sort
     if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
-    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, ranges, D, max_count, point_list);
+    rc = gsb_tile_binning_sort(ctx, s, n, width, height, points_xy, depths, radii, ranges, D, max_count, point_list,
+                               nullptr);
     if (rc != GSB_OK) return rc;
     if (used_tile_path_host) *used_tile_path_host = 1;
   } else {
@@ -252,18 +261,53 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   // read-back so that it runs while the host wakes up and launches the rest.
   int64_t D = 0;
   int max_count = 0;
+  // The rest of the frame -- scatter, per-tile sort, blend -- is queued SPECULATIVELY behind the scan, before the host
+  // knows D: launch sizes do not depend on D, only the buffer capacity and the sort kernel's capacity class do, and
+  // those are taken from the previous frame (with head-room).  tile_scan_kernel checks them on the device and leaves
+  // a go-ahead flag every speculative CTA reads first.  The host then waits for D while the GPU is already blending
+  // (the wait used to leave the GPU idle for 9-10 us per frame: scan -> read-back -> wake-up -> launch); when the
+  // frame does not fit (first frame, the scene grew, a tile list beyond the class) the speculative kernels have done
+  // nothing and the frame continues below as before.
+  bool spec = false;
+  int spec_cap = 0, spec_max = 0;
+  if (ctx->opt.speculate && ctx->opt.binning == 0 && ctx->opt.tile_sort == 3 && ctx->last_num_rendered > 0 && n > 0) {
+    const int64_t cap = ctx->bin_cap < point_list_capacity ? ctx->bin_cap : point_list_capacity;
+    spec_cap = (int)(cap < GSB_MAX_RENDERED ? cap : GSB_MAX_RENDERED);
+    const int want = ctx->last_max_count + ctx->last_max_count / 8;
+    spec_max = want <= 1024 ? 1024 : want <= 2048 ? 2048 : 4096;
+    spec = spec_cap > 0 && ctx->last_max_count <= 4096;
+  }
   {
     if ((rc = gsb_tile_binning_prepare(ctx, s, n, num_tiles)) != GSB_OK) return rc;
     PreBin bin{ctx->tile_count};
     rc = gsb_preprocess_impl(ctx, s, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds,
                              rgb, conic_opacity, ctx->tiles_touched, clamped_state, &bin);
     if (rc != GSB_OK) return rc;
-    if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges)) != GSB_OK) return rc;
+    if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges, spec ? spec_cap : 0, spec ? spec_max : 0)) != GSB_OK)
+      return rc;
+    if (spec) {
+      const int* go = ctx->d_scalars + 6;
+      // (num_rendered only picks the scatter kernel's lanes per Gaussian, max_count the sort kernel's class)
+      rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ranges, ctx->last_num_rendered,
+                                 spec_max, point_list, go);
+      if (rc != GSB_OK) return rc;
+      rc = gsb_blend_forward_impl(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
+                                  final_T, n_contrib, block_masks, go);
+      if (rc != GSB_OK) return rc;
+    }
     // forward.py:755-764: inclusive scan
-    // (point_offsets == NULL: the caller does not want this output; the scan is then left out of the frame --
-    // measured 4-7 us per step, the three scan kernels are not always hidden behind the host's wake-up)
+    // (point_offsets == NULL: the caller does not want this output; the scan is then left out of the frame)
     if (point_offsets && (rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK) return rc;
     if ((rc = gsb_tile_binning_wait(ctx, &D, &max_count)) != GSB_OK) return rc;
+  }
+  ctx->last_num_rendered = D <= GSB_MAX_RENDERED ? D : 0;
+  ctx->last_max_count = max_count;
+  if (spec) {
+    if (D > 0 && D <= spec_cap && max_count <= spec_max) {   // the same test tile_scan_kernel made: the frame is queued
+      if (num_rendered_host) *num_rendered_host = D;
+      return GSB_OK;
+    }
+    ctx->tile_clean = 0;   // the speculative scatter did not run: the counters still hold this frame's counts
   }
   if (num_rendered_host) *num_rendered_host = D;
   if (D > (1LL << 30))  // forward.py:765-767
@@ -279,7 +323,7 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
       // (first frame / the scene grew: the segment buffer grows here, behind the read-back of D)
       if ((rc = gsb_reserve_binning(ctx, s, D)) != GSB_OK) return rc;
       rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ranges, D, max_count,
-                                 point_list);
+                                 point_list, nullptr);
       if (rc != GSB_OK) return rc;
     } else {
       // a tile list too long for the shared-memory sort (or the A/B switch): the reference's own

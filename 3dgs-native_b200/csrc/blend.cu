@@ -63,8 +63,9 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
                          const float2* __restrict__ xy, const float* __restrict__ rgb,
                          const float4* __restrict__ conic_opacity, const float* __restrict__ depths,
                          float* __restrict__ image, float* __restrict__ inv_depth, float* __restrict__ final_T,
-                         int* __restrict__ n_contrib, unsigned* __restrict__ block_masks) {
+                         int* __restrict__ n_contrib, unsigned* __restrict__ block_masks, const int* __restrict__ go) {
   constexpr int NT = 256;
+  if (go && *go == 0) return;   // queued speculatively and the frame does not fit (tilesort.cu, tile_scan_kernel)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
 
@@ -249,10 +250,24 @@ GSB_API int gsb_selftest_block_mask(gsb_ctx* ctx, gsb_stream s, int32_t count, c
   return GSB_OK;
 }
 
+int gsb_blend_forward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
+                           const int32_t* point_list, const float* points_xy, const float* rgb,
+                           const float* conic_opacity, const float* depths, float* image, float* inv_depth,
+                           float* final_T, int32_t* n_contrib, int32_t* block_masks, const int* go);
+
 GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* rgb,
                               const float* conic_opacity, const float* depths, float* image, float* inv_depth,
                               float* final_T, int32_t* n_contrib, int32_t* block_masks) {
+  return gsb_blend_forward_impl(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
+                                final_T, n_contrib, block_masks, nullptr);
+}
+
+// go: device flag checked by every CTA (gsb_forward's speculative launch), or nullptr
+int gsb_blend_forward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, const int32_t* ranges,
+                           const int32_t* point_list, const float* points_xy, const float* rgb,
+                           const float* conic_opacity, const float* depths, float* image, float* inv_depth,
+                           float* final_T, int32_t* n_contrib, int32_t* block_masks, const int* go) {
   if (!ctx) return GSB_ERR_INVALID;
   GSB_REQUIRE(ctx, f && f->width > 0 && f->height > 0, "gsb_blend_forward: bad frame");
   GSB_REQUIRE(ctx, gsb_aligned16(conic_opacity), "gsb_blend_forward: conic_opacity must be 16-byte aligned");
@@ -261,6 +276,6 @@ GSB_API int gsb_blend_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, c
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
   GSB_LAUNCH(ctx, blend_forward_kernel, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
              point_list, reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity),
-             depths, image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks));
+             depths, image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks), go);
   return GSB_OK;
 }

@@ -32,6 +32,7 @@ struct gsb_ctx {
     int blend_cull = 1;  // per-block culling masks in the tile kernels
     int tile_sort = 3;   // 3 (default): one-pass bucket sort by depth (bitonic for tiles > 4096); 0: bitonic network for every tile; 1: per-tile LSD radix sort (bitonic for tiles > 4096); 2: radix when the longest list > 2048
     int bwd_reduce = 2;  // 2 (1 is accepted as a synonym): tensor-core pixel sums; 0: warp-shuffle butterfly with the exact exponential
+    int speculate = 1;   // 1: gsb_forward queues scatter / sort / blend behind the scan without waiting for D (checked on the device); 0: waits first
     int sort_coop = 1;   // 1: gsb_sort_pairs64 sorts inputs of up to num_sms x 12288 pairs in one cooperative launch; 0: three kernels per pass
     int bwd_packed = 1;  // 1: the tensor-core backward accumulates into packed records with vector REDs; 0: nine scalar REDs
   } opt;
@@ -63,6 +64,8 @@ struct gsb_ctx {
   int64_t bwd_acc_cap = 0;
   int32_t* rank_base = nullptr;  // index of a Gaussian's first arrival rank (fused counting pass)
   int64_t n_cap = 0;
+  int64_t last_num_rendered = 0;   // D and the longest tile list of the previous gsb_forward: what the next frame's
+  int last_max_count = 0;          // speculative launch assumes
   cudaEvent_t ev_count = nullptr;  // recorded behind the read-back of D: the host waits on it, not on the stream
   // device + pinned host scalars
   int32_t* d_scalars = nullptr;  // [16]

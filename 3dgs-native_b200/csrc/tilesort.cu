@@ -47,7 +47,7 @@ tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ 
 // frame (gsb_tile_binning_prepare then skips its memset).
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __restrict__ ranges,
-                 int* __restrict__ out_total_max) {
+                 int* __restrict__ out_total_max, const int spec_cap, const int spec_max) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_max[32];
@@ -102,6 +102,9 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
     for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
     out_total_max[0] = s_carry;
     out_total_max[1] = m;
+    // the go-ahead of the kernels gsb_forward queued behind this one WITHOUT waiting for D on the host: they run only
+    // if the frame fits what the host assumed (buffer capacity, the sort kernel's capacity class)
+    out_total_max[2] = (s_carry > 0 && s_carry <= spec_cap && m <= spec_max) ? 1 : 0;
   }
 }
 
@@ -114,7 +117,8 @@ template <int kScatterLanes>
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
                     const int* __restrict__ radii, int grid_x, int grid_y, const int2* __restrict__ ranges,
-                    int* __restrict__ tile_count, unsigned long long* __restrict__ binned) {
+                    int* __restrict__ tile_count, unsigned long long* __restrict__ binned, const int* __restrict__ go) {
+  if (go && *go == 0) return;   // queued speculatively and the frame does not fit (see tile_scan_kernel)
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int gid = (int)(t / kScatterLanes), sub = (int)(t % kScatterLanes);
   if (gid >= n) return;
@@ -441,9 +445,10 @@ __device__ __forceinline__ void tile_bucket_segment(const int2 rg, const unsigne
 template <int MAXCAP>
 __global__ void __launch_bounds__(256)
 tile_bucket_kernel(const int2* __restrict__ ranges, const unsigned long long* __restrict__ binned,
-                   int* __restrict__ point_list, int lo, int hi) {
+                   int* __restrict__ point_list, int lo, int hi, const int* __restrict__ go) {
   extern __shared__ __align__(16) unsigned long long s_dst[];      // [CAP] entries in bucket order + [CAP] cursors
   __shared__ unsigned s_min[8], s_max[8], s_wtot[8];
+  if (go && *go == 0) return;   // queued speculatively and the frame does not fit (see tile_scan_kernel)
   const int2 rg = ranges[blockIdx.x];
   const int count = rg.y - rg.x;
   if (count <= lo || count > hi) return;
@@ -478,9 +483,9 @@ int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles)
 }
 
 // scan the counters into ranges, start the read-back of (D, max count) and mark it with an event
-int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges) {
+int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges, int spec_cap, int spec_max) {
   GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
-             ctx->d_scalars + 4);
+             ctx->d_scalars + 4, spec_cap, spec_max);
   GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
   return GSB_OK;
@@ -505,24 +510,26 @@ int gsb_tile_binning_count(gsb_ctx* ctx, cudaStream_t s, int n, int width, int h
   if (n > 0)
     GSB_LAUNCH(ctx, tile_count_kernel, (int)gsb_div_up(n, 256), 256, 0, s, n, reinterpret_cast<const float2*>(points_xy),
                radii, gx, gy, ctx->tile_count);
-  if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges)) != GSB_OK) return rc;
+  if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges, 0, 0)) != GSB_OK) return rc;
   return gsb_tile_binning_wait(ctx, num_rendered_host, max_count_host);
 }
 
 // precondition (checked by the caller): ctx->bin_cap >= num_rendered and the counters hold this frame's counts
+// go != nullptr: queued speculatively (num_rendered / max_count are the host's assumptions; the kernels check *go);
+// only the one-pass bucket sort with max_count <= 4096 may be queued that way.
 int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int height, const float* points_xy,
                           const float* depths, const int32_t* radii, const int32_t* ranges, int64_t num_rendered,
-                          int max_count, int32_t* point_list) {
+                          int max_count, int32_t* point_list, const int* go) {
   const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
   const int num_tiles = gx * gy;
   unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
   const int2* rg = reinterpret_cast<const int2*>(ranges);
   if (num_rendered > 8 * (int64_t)n) {
     GSB_LAUNCH(ctx, tile_scatter_kernel<8>, (unsigned)gsb_div_up((int64_t)n * 8, 256), 256, 0, s, n,
-               reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned);
+               reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned, go);
   } else {
     GSB_LAUNCH(ctx, tile_scatter_kernel<1>, (unsigned)gsb_div_up(n, 256), 256, 0, s, n,
-               reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned);
+               reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned, go);
   }
   ctx->tile_clean = (int64_t)num_tiles * kCntStride;   // every counter is back at zero when the scatter pass has run
   // Per-tile sort: the bitonic network (O(n log^2 n), pure register / shuffle / shared-memory compare-exchange) or
@@ -549,11 +556,11 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   if (ctx->opt.tile_sort == 3) {
     // one-pass bucket sort for tiles of up to 4096 entries (12 bytes of shared memory per entry of the capacity)
     if (max_count <= 1024) {
-      GSB_LAUNCH(ctx, tile_bucket_kernel<1024>, num_tiles, 256, 1024 * 12, s, rg, binned, point_list, 0, 1024);
+      GSB_LAUNCH(ctx, tile_bucket_kernel<1024>, num_tiles, 256, 1024 * 12, s, rg, binned, point_list, 0, 1024, go);
     } else if (max_count <= 2048) {
-      GSB_LAUNCH(ctx, tile_bucket_kernel<2048>, num_tiles, 256, 2048 * 12, s, rg, binned, point_list, 0, 2048);
+      GSB_LAUNCH(ctx, tile_bucket_kernel<2048>, num_tiles, 256, 2048 * 12, s, rg, binned, point_list, 0, 2048, go);
     } else {
-      GSB_LAUNCH(ctx, tile_bucket_kernel<kRadixCap>, num_tiles, 256, kRadixCap * 12, s, rg, binned, point_list, 0, kRadixCap);
+      GSB_LAUNCH(ctx, tile_bucket_kernel<kRadixCap>, num_tiles, 256, kRadixCap * 12, s, rg, binned, point_list, 0, kRadixCap, go);
     }
     if (max_count <= kRadixCap) return GSB_OK;
     bitonic_lo = kRadixCap;

@@ -149,3 +149,31 @@ def test_both_binning_paths_match_oracle(L, oracle, n, w, h, smin, smax, heavy):
         for k in ("point_offsets", "point_list", "ranges", "n_contrib", "radii"):
             assert np.array_equal(buf[k].cpu().numpy().reshape(ob[k].shape), ob[k]), (mode, tile_sort, k, longest)
         assert np.abs(img.cpu().numpy() - o_img).max() <= 1e-4
+
+
+def test_speculative_frames_match_waiting_frames(L):
+    """gsb_forward queues scatter / sort / blend behind the tile scan without waiting for D, on assumptions taken from
+    the previous frame and checked on the device.  A sequence of frames whose D and longest tile list jump up and
+    down must give, frame by frame, exactly what the waiting path gives."""
+    import gsb200  # noqa: F401
+    from gsb200 import forward
+    seq = [(4000, 160, 96, 0.01, 0.05), (4000, 160, 96, 0.01, 0.05), (9000, 64, 48, 0.1, 0.4), (9000, 64, 48, 0.1, 0.4),
+           (300, 160, 96, 0.01, 0.03), (20000, 320, 240, 0.005, 0.05), (20000, 320, 240, 0.005, 0.05),
+           (9000, 32, 32, 0.5, 1.5), (4000, 160, 96, 0.01, 0.05)]
+    ctx = L.context()
+    res = {}
+    for spec in (0, 1):
+        ctx.set_option("speculate", spec)
+        try:
+            out = []
+            for (n, w, h, smin, smax) in seq:
+                img, dep, buf = forward.render_gaussians(**_scene(n, w, h, smin, smax, n))
+                out.append((img.cpu().numpy(), dep.cpu().numpy(),
+                            {k: buf[k].cpu().numpy() for k in ("point_list", "ranges", "n_contrib", "final_Ts")}))
+        finally:
+            ctx.set_option("speculate", 1)
+        res[spec] = out
+    for (a_img, a_dep, a_buf), (b_img, b_dep, b_buf) in zip(res[0], res[1]):
+        assert np.array_equal(a_img, b_img) and np.array_equal(a_dep, b_dep)
+        for k in a_buf:
+            assert np.array_equal(a_buf[k], b_buf[k]), k

@@ -73,9 +73,17 @@ int64_t gsb_launch_count(gsb_ctx* ctx);
  *   "bwd_reduce" = 2 (default; 1 is a synonym): the backward tile kernel sums the per-pixel terms over a warp's
  *                  pixel block with TF32 tensor-core products; 0: warp-shuffle butterfly (and the contract's
  *                  exponential instead of MUFU: the slow, independent implementation the fast one is tested beside)
- *   "tile_sort"  = 2 (default): per-tile shared-memory LSD radix sort when the frame's longest tile list exceeds
- *                  2048 entries, bitonic network otherwise; 0: always bitonic; 1: always radix (tiles of more
- *                  than 4096 entries still go to the bitonic kernel)
+ *   "tile_sort"  = 3 (default): one-pass bucket sort of every tile's segment by depth (order-preserving map of the
+ *                  depth bits onto >= n buckets, shared-memory atomics, every entry ranks itself inside its bucket;
+ *                  bitonic network for degenerate depth distributions and for tiles of more than 4096 entries);
+ *                  0: always the bitonic network; 1: always the per-tile LSD radix sort; 2: radix when the frame's
+ *                  longest tile list exceeds 2048 entries, bitonic otherwise (round 2's first default)
+ *   "speculate"  = 1 (default): gsb_forward queues scatter / per-tile sort / blend behind the tile scan without
+ *                  waiting for num_rendered on the host -- the previous frame's capacity and list-length class are
+ *                  assumed and checked on the device; a frame that does not fit continues on the waiting path;
+ *                  0: always wait first
+ *   "sort_coop"  = 1 (default): gsb_sort_pairs64 sorts inputs of up to num_sms x 12288 pairs with all passes in ONE
+ *                  cooperative launch; 0: three kernels per 8-bit pass (any size)
  *   "binning"    = 0 (default): gsb_forward bins by tile with a counting sort and sorts every tile's
  *                  segment in shared memory; 1: duplicate-with-keys + global 64-bit radix sort */
 int gsb_set_option(gsb_ctx* ctx, const char* name, int value);

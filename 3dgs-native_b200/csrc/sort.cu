@@ -611,13 +611,23 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
     (void)fn; (void)args;
     GSB_CUDA(ctx, cudaGetLastError());
 #else
-    GSB_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kCoopThreads), args,
-                                              wide ? sizeof(CoopSmem<9>) : sizeof(CoopSmem<8>), s));
+    const cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kCoopThreads), args,
+                                                       wide ? sizeof(CoopSmem<9>) : sizeof(CoopSmem<8>), s);
+    if (ce == cudaErrorCooperativeLaunchTooLarge) {
+      // fewer SMs than the device reports can hold CTAs of this kernel (a partitioned device): nothing was launched;
+      // this context sorts with the three-kernel path from now on
+      cudaGetLastError();
+      ctx->coop_launch = false;
+    } else {
+      GSB_CUDA(ctx, ce);
 #endif
-    ctx->launches += 1;
-    const int coop_passes = wide ? (key_bits + 8) / 9 : passes;
-    *result_in_second = (coop_passes & 1) != 0;
-    return GSB_OK;
+      ctx->launches += 1;
+      const int coop_passes = wide ? (key_bits + 8) / 9 : passes;
+      *result_in_second = (coop_passes & 1) != 0;
+      return GSB_OK;
+#ifndef GSB_COOP_PLAIN_LAUNCH
+    }
+#endif
   }
   int64_t chunk;
   const int nb = plan(ctx, n, &chunk);

@@ -80,11 +80,28 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(1)
     keys = torch.randint(0, 1 << 40, (D,), device="cuda", generator=g, dtype=torch.int64)
     vals = torch.arange(D, device="cuda", dtype=torch.int32)
-    ctx.check(_lib.lib().gsb_sort_pairs64(ctx.h, _lib.stream_ptr(ctx.device_index), _lib.ptr(keys), _lib.ptr(vals), None,
-                                          None, D, 0, 40))
-    torch.cuda.synchronize()
-    assert bool((keys[1:] >= keys[:-1]).all())
+    for coop in (1, 0):                    # one cooperative launch (9-bit digits: 40 bits = 5 passes) / three kernels per pass
+        ctx.set_option("sort_coop", coop)
+        k2, v2 = keys.clone(), vals.clone()
+        ctx.check(_lib.lib().gsb_sort_pairs64(ctx.h, _lib.stream_ptr(ctx.device_index), _lib.ptr(k2), _lib.ptr(v2), None,
+                                              None, D, 0, 40))
+        torch.cuda.synchronize()
+        assert bool((k2[1:] >= k2[:-1]).all()) and bool(torch.equal(keys[v2.long()], k2))
+    ctx.set_option("sort_coop", 1)
     print("radix sort ok")
+    # degenerate depths (one plane facing the camera): the bucket sort's bitonic fallback; speculative and waiting frames
+    kw = scene.render_kwargs(params, cam)
+    view = np.asarray(kw["viewmatrix"], dtype=np.float64).reshape(4, 4)
+    m = np.asarray(kw["means3D"], dtype=np.float64)
+    m -= np.outer((m - m[0]) @ view[:3, 2], view[:3, 2])
+    kw["means3D"] = m.astype(np.float32)
+    for spec in (1, 0, 1):
+        ctx.set_option("speculate", spec)
+        forward.render_gaussians(**kw)
+        forward.render_gaussians(**scene.render_kwargs(params, cam))
+    ctx.set_option("speculate", 1)
+    torch.cuda.synchronize()
+    print("degenerate depths / speculation ok")
 
 
 if __name__ == "__main__":

@@ -136,6 +136,9 @@ GSB_API int gsb_destroy(gsb_ctx* ctx) {
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->rank_base) cudaFree(ctx->rank_base);
   if (ctx->sort_coop_state) cudaFree(ctx->sort_coop_state);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->bwd_acc) cudaFree(ctx->bwd_acc);
   if (ctx->bwd_acc_stage) cudaFree(ctx->bwd_acc_stage);
   if (ctx->ev_count) cudaEventDestroy(ctx->ev_count);
@@ -285,6 +288,24 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
     if (rc != GSB_OK) return rc;
     if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges, spec ? spec_cap : 0, spec ? spec_max : 0)) != GSB_OK)
       return rc;
+    bool offsets_on_side = false;
+    if (spec && point_offsets) {
+      // forward.py:755-764, the inclusive scan of tiles_touched -- an OUTPUT of the operator, not an input of this
+      // binning: three small latency-bound kernels.  They used to run in the shadow of the host's wait; now that the
+      // wait no longer idles the GPU they go to a side stream, beside the scatter / sort / blend, and the caller's
+      // stream joins them at the end of the queue.
+      if (!ctx->side_stream) {
+        GSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        GSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        GSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+      }
+      GSB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+      GSB_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+      if ((rc = gsb_scan_tiles(ctx, (gsb_stream)ctx->side_stream, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK)
+        return rc;
+      GSB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+      offsets_on_side = true;
+    }
     if (spec) {
       const int* go = ctx->d_scalars + 6;
       // (num_rendered only picks the scatter kernel's lanes per Gaussian, max_count the sort kernel's class)
@@ -294,10 +315,13 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
       rc = gsb_blend_forward_impl(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
                                   final_T, n_contrib, block_masks, go);
       if (rc != GSB_OK) return rc;
+      if (offsets_on_side) GSB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
     // forward.py:755-764: inclusive scan
     // (point_offsets == NULL: the caller does not want this output; the scan is then left out of the frame)
-    if (point_offsets && (rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK) return rc;
+    if (point_offsets && !offsets_on_side &&
+        (rc = gsb_scan_tiles(ctx, s_, n, ctx->tiles_touched, point_offsets, nullptr)) != GSB_OK)
+      return rc;
     if ((rc = gsb_tile_binning_wait(ctx, &D, &max_count)) != GSB_OK) return rc;
   }
   ctx->last_num_rendered = D <= GSB_MAX_RENDERED ? D : 0;

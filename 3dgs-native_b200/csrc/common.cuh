@@ -66,6 +66,8 @@ struct gsb_ctx {
   int64_t n_cap = 0;
   int64_t last_num_rendered = 0;   // D and the longest tile list of the previous gsb_forward: what the next frame's
   int last_max_count = 0;          // speculative launch assumes
+  cudaStream_t side_stream = nullptr;   // gsb_forward: the point_offsets scan beside the speculative kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_count = nullptr;  // recorded behind the read-back of D: the host waits on it, not on the stream
   // device + pinned host scalars
   int32_t* d_scalars = nullptr;  // [16]

@@ -169,6 +169,10 @@ GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
     ctx->opt.tile_sort = value;
     return GSB_OK;
   }
+  if (!strcmp(name, "pdl") && (value == 0 || value == 1)) {
+    ctx->opt.pdl = value;
+    return GSB_OK;
+  }
   if (!strcmp(name, "speculate") && (value == 0 || value == 1)) {
     ctx->opt.speculate = value;
     return GSB_OK;

@@ -65,6 +65,8 @@ blend_forward_kernel(const BlendParams P, const int2* __restrict__ ranges, const
                          float* __restrict__ image, float* __restrict__ inv_depth, float* __restrict__ final_T,
                          int* __restrict__ n_contrib, unsigned* __restrict__ block_masks, const int* __restrict__ go) {
   constexpr int NT = 256;
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   if (go && *go == 0) return;   // queued speculatively and the frame does not fit (tilesort.cu, tile_scan_kernel)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
@@ -274,7 +276,7 @@ int gsb_blend_forward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, cons
   cudaStream_t s = (cudaStream_t)s_;
   BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
-  GSB_LAUNCH(ctx, blend_forward_kernel, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
+  GSB_LAUNCH_PDL(ctx, blend_forward_kernel, grid, 256, sizeof(FwdSmem), s, P, reinterpret_cast<const int2*>(ranges),
              point_list, reinterpret_cast<const float2*>(points_xy), rgb, reinterpret_cast<const float4*>(conic_opacity),
              depths, image, inv_depth, final_T, n_contrib, reinterpret_cast<unsigned*>(block_masks), go);
   return GSB_OK;

@@ -374,6 +374,8 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
                           const unsigned* __restrict__ block_masks, float* __restrict__ acc_packed) {
   constexpr int NT = 256, NW = 8;
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
@@ -592,6 +594,8 @@ struct ZeroJob {
   long long n[4];  // floats
 };
 __global__ void __launch_bounds__(256) zero_arrays_kernel(const ZeroJob job) {
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -697,7 +701,7 @@ static int launch_backward_mma(gsb_ctx* ctx, cudaStream_t s, const BlendParams& 
     attr_set = true;
   }
 #define GSB_BWD_MMA(PK)                                                                                                    \
-  GSB_LAUNCH(ctx, (blend_backward_mma_kernel<PK>), grid, 256, sizeof(BwdSmem), s, P,                                        \
+  GSB_LAUNCH_PDL(ctx, (blend_backward_mma_kernel<PK>), grid, 256, sizeof(BwdSmem), s, P,                                        \
              reinterpret_cast<const int2*>(ranges), point_list, reinterpret_cast<const float2*>(points_xy),               \
              reinterpret_cast<const float4*>(conic_opacity), rgb, final_T, n_contrib, dL_dpixels, dL_dmean2D, dL_dconic,  \
              dL_dopacity, dL_dcolor, masks, packed)
@@ -718,7 +722,7 @@ int gsb_blend_backward_packed(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, 
   for (int a = 0; a < 4; ++a) job.p[a] = packed, job.n[a] = 0;
   job.n[0] = 12LL * n;
   const long long blocks = gsb_div_up(3LL * n, 256);  // one 16-byte store per thread
-  GSB_LAUNCH(ctx, zero_arrays_kernel, (unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, s, job);
+  GSB_LAUNCH_PDL(ctx, zero_arrays_kernel, (unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, s, job);
   BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);
   return launch_backward_mma(ctx, s, P, grid, ranges, point_list, points_xy, conic_opacity, rgb, final_T, n_contrib,
@@ -757,7 +761,7 @@ GSB_API int gsb_blend_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, 
     job.p[2] = dL_dopacity, job.n[2] = (long long)n;
     job.p[3] = dL_dcolor, job.n[3] = 3LL * n;
     const long long blocks = gsb_div_up(n, 256);  // one 16-byte store per thread and array
-    GSB_LAUNCH(ctx, zero_arrays_kernel, (unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, s, job);
+    GSB_LAUNCH_PDL(ctx, zero_arrays_kernel, (unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, s, job);
   }
   BlendParams P = make_blend_params(ctx, f);
   dim3 grid(P.grid_x, (f->height + kTile - 1) / kTile);

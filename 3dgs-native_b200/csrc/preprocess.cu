@@ -30,6 +30,8 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
                   float* __restrict__ cov3Ds, float* __restrict__ rgb, float4* __restrict__ conic_opacity,
                   int* __restrict__ tiles_touched, float* __restrict__ clamped_state, const PreBin bin) {
   __shared__ float s_sh[kPreThreads * kShStride];
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   const int base = blockIdx.x * kPreThreads;
   const int tid = threadIdx.x;
   const int rows = min(kPreThreads, n - base);
@@ -285,11 +287,11 @@ int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_
   gsb_make_framek(f, &k);
   int grid = (int)gsb_div_up(n, kPreThreads);
   if (bin) {
-    GSB_LAUNCH(ctx, preprocess_kernel<true>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
+    GSB_LAUNCH_PDL(ctx, preprocess_kernel<true>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
                radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
                reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, *bin);
   } else {
-    GSB_LAUNCH(ctx, preprocess_kernel<false>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
+    GSB_LAUNCH_PDL(ctx, preprocess_kernel<false>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
                radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
                reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, PreBin{});
   }

@@ -39,6 +39,8 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
                            float4* __restrict__ dL_drot, float* __restrict__ dL_dcov3D_out,
                            const float4* __restrict__ packed, float* __restrict__ dL_dopacity_out) {
   __shared__ float s_sh[kThreads * kShStride];
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   const int base = blockIdx.x * kThreads;
   const int tid = threadIdx.x;
   const int rows = min(kThreads, n - base);

@@ -51,6 +51,8 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_max[32];
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
   int my_max = 0;
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int n, const float2* __restrict__ xy, const float* __restrict__ depths,
                     const int* __restrict__ radii, int grid_x, int grid_y, const int2* __restrict__ ranges,
                     int* __restrict__ tile_count, unsigned long long* __restrict__ binned, const int* __restrict__ go) {
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   if (go && *go == 0) return;   // queued speculatively and the frame does not fit (see tile_scan_kernel)
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int gid = (int)(t / kScatterLanes), sub = (int)(t % kScatterLanes);
@@ -448,6 +452,8 @@ tile_bucket_kernel(const int2* __restrict__ ranges, const unsigned long long* __
                    int* __restrict__ point_list, int lo, int hi, const int* __restrict__ go) {
   extern __shared__ __align__(16) unsigned long long s_dst[];      // [CAP] entries in bucket order + [CAP] cursors
   __shared__ unsigned s_min[8], s_max[8], s_wtot[8];
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
   if (go && *go == 0) return;   // queued speculatively and the frame does not fit (see tile_scan_kernel)
   const int2 rg = ranges[blockIdx.x];
   const int count = rg.y - rg.x;
@@ -484,7 +490,7 @@ int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles)
 
 // scan the counters into ranges, start the read-back of (D, max count) and mark it with an event
 int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges, int spec_cap, int spec_max) {
-  GSB_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
+  GSB_LAUNCH_PDL(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
              ctx->d_scalars + 4, spec_cap, spec_max);
   GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
@@ -525,10 +531,10 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   unsigned long long* binned = reinterpret_cast<unsigned long long*>(ctx->keys_a);
   const int2* rg = reinterpret_cast<const int2*>(ranges);
   if (num_rendered > 8 * (int64_t)n) {
-    GSB_LAUNCH(ctx, tile_scatter_kernel<8>, (unsigned)gsb_div_up((int64_t)n * 8, 256), 256, 0, s, n,
+    GSB_LAUNCH_PDL(ctx, tile_scatter_kernel<8>, (unsigned)gsb_div_up((int64_t)n * 8, 256), 256, 0, s, n,
                reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned, go);
   } else {
-    GSB_LAUNCH(ctx, tile_scatter_kernel<1>, (unsigned)gsb_div_up(n, 256), 256, 0, s, n,
+    GSB_LAUNCH_PDL(ctx, tile_scatter_kernel<1>, (unsigned)gsb_div_up(n, 256), 256, 0, s, n,
                reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned, go);
   }
   ctx->tile_clean = (int64_t)num_tiles * kCntStride;   // every counter is back at zero when the scatter pass has run
@@ -556,11 +562,11 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
   if (ctx->opt.tile_sort == 3) {
     // one-pass bucket sort for tiles of up to 4096 entries (12 bytes of shared memory per entry of the capacity)
     if (max_count <= 1024) {
-      GSB_LAUNCH(ctx, tile_bucket_kernel<1024>, num_tiles, 256, 1024 * 12, s, rg, binned, point_list, 0, 1024, go);
+      GSB_LAUNCH_PDL(ctx, tile_bucket_kernel<1024>, num_tiles, 256, 1024 * 12, s, rg, binned, point_list, 0, 1024, go);
     } else if (max_count <= 2048) {
-      GSB_LAUNCH(ctx, tile_bucket_kernel<2048>, num_tiles, 256, 2048 * 12, s, rg, binned, point_list, 0, 2048, go);
+      GSB_LAUNCH_PDL(ctx, tile_bucket_kernel<2048>, num_tiles, 256, 2048 * 12, s, rg, binned, point_list, 0, 2048, go);
     } else {
-      GSB_LAUNCH(ctx, tile_bucket_kernel<kRadixCap>, num_tiles, 256, kRadixCap * 12, s, rg, binned, point_list, 0, kRadixCap, go);
+      GSB_LAUNCH_PDL(ctx, tile_bucket_kernel<kRadixCap>, num_tiles, 256, kRadixCap * 12, s, rg, binned, point_list, 0, kRadixCap, go);
     }
     if (max_count <= kRadixCap) return GSB_OK;
     bitonic_lo = kRadixCap;

@@ -82,6 +82,9 @@ int64_t gsb_launch_count(gsb_ctx* ctx);
  *                  waiting for num_rendered on the host -- the previous frame's capacity and list-length class are
  *                  assumed and checked on the device; a frame that does not fit continues on the waiting path;
  *                  0: always wait first
+ *   "pdl"        = 1 (default): the kernels of a frame / training step are launched as programmatic dependents of
+ *                  the kernel in front of them (they reach the SMs during its last wave and wait there for its
+ *                  completion: launch latency and prologue hidden, never a data dependency); 0: plain launches
  *   "sort_coop"  = 1 (default): gsb_sort_pairs64 sorts inputs of up to num_sms x 12288 pairs with all passes in ONE
  *                  cooperative launch; 0: three kernels per 8-bit pass (any size)
  *   "binning"    = 0 (default): gsb_forward bins by tile with a counting sort and sorts every tile's

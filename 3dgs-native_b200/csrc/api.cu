@@ -290,14 +290,12 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
     rc = gsb_preprocess_impl(ctx, s, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds,
                              rgb, conic_opacity, ctx->tiles_touched, clamped_state, &bin);
     if (rc != GSB_OK) return rc;
-    if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges, spec ? spec_cap : 0, spec ? spec_max : 0)) != GSB_OK)
-      return rc;
     bool offsets_on_side = false;
     if (spec && point_offsets) {
       // forward.py:755-764, the inclusive scan of tiles_touched -- an OUTPUT of the operator, not an input of this
       // binning: three small latency-bound kernels.  They used to run in the shadow of the host's wait; now that the
-      // wait no longer idles the GPU they go to a side stream, beside the scatter / sort / blend, and the caller's
-      // stream joins them at the end of the queue.
+      // wait no longer idles the GPU they go to a side stream, forked here behind preprocess, and run beside the
+      // scan / scatter / sort / blend; the caller's stream joins them at the end of the queue.
       if (!ctx->side_stream) {
         GSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
         GSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -310,6 +308,8 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
       GSB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
       offsets_on_side = true;
     }
+    if ((rc = gsb_tile_binning_scan_async(ctx, s, num_tiles, ranges, spec ? spec_cap : 0, spec ? spec_max : 0)) != GSB_OK)
+      return rc;
     if (spec) {
       const int* go = ctx->d_scalars + 6;
       // (num_rendered only picks the scatter kernel's lanes per Gaussian, max_count the sort kernel's class)

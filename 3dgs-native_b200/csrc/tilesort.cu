@@ -47,7 +47,8 @@ tile_count_kernel(int n, const float2* __restrict__ xy, const int* __restrict__ 
 // frame (gsb_tile_binning_prepare then skips its memset).
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __restrict__ ranges,
-                 int* __restrict__ out_total_max, const int spec_cap, const int spec_max) {
+                 int* __restrict__ out_total_max, volatile int* __restrict__ host_total_max, const int spec_cap,
+                 const int spec_max) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_max[32];
@@ -107,6 +108,11 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
     // the go-ahead of the kernels gsb_forward queued behind this one WITHOUT waiting for D on the host: they run only
     // if the frame fits what the host assumed (buffer capacity, the sort kernel's capacity class)
     out_total_max[2] = (s_carry > 0 && s_carry <= spec_cap && m <= spec_max) ? 1 : 0;
+    // D and the longest list go straight to the host's (mapped, pinned) scalars: no copy operation sits in the
+    // stream between this kernel and the scatter pass (it cost ~2 us and broke the chain of dependent launches)
+    host_total_max[0] = s_carry;
+    host_total_max[1] = m;
+    __threadfence_system();
   }
 }
 
@@ -491,11 +497,13 @@ int gsb_tile_binning_prepare(gsb_ctx* ctx, cudaStream_t s, int n, int num_tiles)
 // scan the counters into ranges, start the read-back of (D, max count) and mark it with an event
 int gsb_tile_binning_scan_async(gsb_ctx* ctx, cudaStream_t s, int num_tiles, int32_t* ranges, int spec_cap, int spec_max) {
   GSB_LAUNCH_PDL(ctx, tile_scan_kernel, 1, 1024, 0, s, num_tiles, ctx->tile_count, reinterpret_cast<int2*>(ranges),
-             ctx->d_scalars + 4, spec_cap, spec_max);
-  GSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_scalars + 4, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
+             ctx->d_scalars + 4, ctx->h_scalars + 4, spec_cap, spec_max);
+  // speculative frames record the event behind the scatter pass: an event between the two
+  // kernels would also break the dependent-launch chain, and the host is in no hurry while the GPU has the blend ahead
+  if (spec_cap <= 0) GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));
   return GSB_OK;
 }
+
 
 // the one host wait of a frame: on the event, so work queued behind the read-back keeps running
 int gsb_tile_binning_wait(gsb_ctx* ctx, int64_t* num_rendered_host, int* max_count_host) {
@@ -538,6 +546,7 @@ int gsb_tile_binning_sort(gsb_ctx* ctx, cudaStream_t s, int n, int width, int he
                reinterpret_cast<const float2*>(points_xy), depths, radii, gx, gy, rg, ctx->tile_count, binned, go);
   }
   ctx->tile_clean = (int64_t)num_tiles * kCntStride;   // every counter is back at zero when the scatter pass has run
+  if (go) GSB_CUDA(ctx, cudaEventRecord(ctx->ev_count, s));   // speculative frame: the host's wait for D ends here
   // Per-tile sort: the bitonic network (O(n log^2 n), pure register / shuffle / shared-memory compare-exchange) or
   // the O(n) shared-memory LSD radix sort for tiles of up to 4096 entries (longer ones always go to the bitonic
   // kernel; each kernel skips the other's tiles).  Measured on a B200, whole forward, L2 flushed:

@@ -9,7 +9,12 @@ from . import _lib
 
 
 def l1_loss_and_gradients(rendered, target, lambda_dssim=0.0, out_grad=None, out_sum=None):
-    """Returns (loss_sum_device[1] float64, pixel_grad[H,W,3]).  loss = sum / (3*H*W)."""
+    """Returns (loss_sum_device[1] float64, pixel_grad[H,W,3]).  loss = sum / (3*H*W).
+
+    ``out_grad`` / ``out_sum`` (not reference arguments): preallocated outputs.  ``out_sum`` may also be a one-element
+    float64 tensor in PINNED HOST memory: the kernel then writes the sum straight there (8 bytes over PCIe; unified
+    addressing), and a host that waits for an event recorded behind this call reads it without any copy operation in
+    the stream -- a device-to-host cudaMemcpyAsync of 8 bytes costs the stream about 10 us."""
     ctx = _lib.context()
     dev = torch.device("cuda", ctx.device_index)
     r = _lib.to_device(rendered, device=dev)

@@ -594,7 +594,13 @@ def ours(args):
             if pending is not None:
                 consume(pending)                     # the previous step's loss (its copy finished long ago)
             main.wait_event(ready)
-            loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0)
+            # D2H of the step's result, every step: the loss kernel writes its sum STRAIGHT into pinned host memory
+            # (out_sum may be a pinned host tensor: 8 bytes over PCIe, no copy operation in the stream -- a D2H
+            # cudaMemcpyAsync of 8 bytes costs the stream ~10 us, tools/e2e_variants.py); the host consumes the
+            # value one step later (after the next forward call), behind an event recorded at the end of this step,
+            # so preparing the next step overlaps this step's Adam.  All K values are read before the clock stops.
+            slot = it & 1
+            _, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0, out_sum=loss_host[slot])
             if world > 1:
                 # multi-GPU: the gradients land directly in the symmetric flat buffer (backward's `out`),
                 # and the public exchange step (fused NVLink reduction + Adam + parameter broadcast, or
@@ -611,11 +617,6 @@ def ours(args):
                                  it, P["positions"], P["scales"], P["rotations"], P["opacities"], P["shs"],
                                  M["positions"], M["scales"], M["rotations"], M["opacities"], M["shs"],
                                  V["positions"], V["scales"], V["rotations"], V["opacities"], V["shs"])
-            # D2H of the step's result, every step, into pinned memory; the host consumes the value one
-            # step later (after the next forward call), so preparing the next step overlaps this step's
-            # Adam instead of waiting for it.  All K values are read before the clock stops.
-            slot = it & 1
-            loss_host[slot].copy_(loss_sum, non_blocking=True)
             loss_ready[slot].record(main)
             return slot
 
@@ -650,7 +651,8 @@ def ours(args):
                "api": ("forward.render_gaussians + loss.l1_loss_and_gradients + backward.backward + optimizer.adam_update"
                        if world == 1 else "forward.render_gaussians + loss.l1_loss_and_gradients + backward.backward(out="
                        "flat gradient buffer) + Trainer.exchange_and_step"),
-               "loss_readback": "D2H into pinned memory every step, consumed by the host one step later; all K read "
+               "loss_readback": "every step the loss kernel writes its sum straight into pinned host memory (8 bytes over "
+                                "PCIe, no copy operation); consumed by the host one step later behind an event; all K read "
                                 "inside the timed region", "last_loss": losses[-1]}
 
     # ---- per-stage table + roofline of the dominant kernel (rank 0; the other ranks wait at the next barrier) ----

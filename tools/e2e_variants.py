@@ -51,7 +51,10 @@ def main():
                 tgt.copy_(pinned, non_blocking=True)
             else:
                 tgt = resident
-            loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0)
+            if readback == "mapped":   # the loss kernel writes its sum straight into pinned host memory
+                loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0, out_sum=loss_host[it & 1])
+            else:
+                loss_sum, dpix = gl.l1_loss_and_gradients(img, tgt, 0.0)
             g = gb.backward(**scene.backward_kwargs(P, cam, buf, dpix, background=bg))
             gopt.adam_update(g["dL_dmean3D"], g["dL_dscale"], g["dL_drot"], g["dL_dopacity"], g["dL_dshs"], n, 1e-6, 5e-7,
                              5e-7, 5e-7, 2e-7, 0.9, 0.999, 1e-8, it, P["positions"], P["scales"], P["rotations"],
@@ -59,6 +62,9 @@ def main():
                              M["shs"], V["positions"], V["scales"], V["rotations"], V["opacities"], V["shs"])
             if readback == "async":
                 loss_host[it & 1].copy_(loss_sum, non_blocking=True)
+                loss_ready[it & 1].record(main_s)
+                pending = it & 1
+            elif readback == "mapped":
                 loss_ready[it & 1].record(main_s)
                 pending = it & 1
             elif readback == "sync":
@@ -79,7 +85,7 @@ def main():
         dt = (time.perf_counter() - t0) / 30 * 1e6
     print(f"trainer (resident state, preallocated buffers)  {dt:8.1f} us/step")
     for h2d in ("none", "side", "main"):
-        for rb in ("none", "async", "sync"):
+        for rb in ("none", "async", "mapped", "sync"):
             run(h2d, rb, 8)
             print(f"h2d={h2d:5s} readback={rb:5s}  {run(h2d, rb):8.1f} us/step")
 

@@ -410,11 +410,10 @@ static int backward_impl(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_
   // backward.py:1155-1182
   rc = gsb_preprocess_backward_impl(ctx, s, f, n, means, radii, shs, scales, rotations, cov3Ds, clamped_state,
                                     dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, dL_drot, nullptr,
-                                    sh_compact, packed ? ctx->bwd_acc : nullptr, dL_dopacity);
-  if (rc != GSB_OK) return rc;
-  // backward.py:1119,1195: the returned dL_dcov3D is a fresh zero buffer no kernel writes
-  if (dL_dcov3D) GSB_CUDA(ctx, cudaMemsetAsync(dL_dcov3D, 0, sizeof(float) * 6 * (size_t)n, s));
-  return GSB_OK;
+                                    sh_compact, packed ? ctx->bwd_acc : nullptr, dL_dopacity,
+                                    dL_dcov3D /* backward.py:1119,1195: returned as zeros; written by the same kernel
+                                                 (a memset was a stream operation between this kernel and Adam) */);
+  return rc;
 }
 
 GSB_API int gsb_backward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t n, const float* means,

@@ -389,7 +389,7 @@ int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* 
                                  const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D, float* dL_dshs,
                                  float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact,
                                  const float* packed /* may be null: see preprocess_backward_kernel<.., PACKED> */,
-                                 float* dL_dopacity_out);
+                                 float* dL_dopacity_out, float* zero_cov3D /* may be null: [6 n] written as zeros */);
 // the backward tile kernel accumulating into the packed 12-float records of `packed` (zeroed here)
 int gsb_blend_backward_packed(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const int32_t* ranges,
                               const int32_t* point_list, const float* points_xy, const float* conic_opacity,

@@ -37,7 +37,8 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
                            const float* __restrict__ dL_dconic, const float* __restrict__ dL_dcolor,
                            float* __restrict__ dL_dmean3D, float* __restrict__ dL_dshs, float* __restrict__ dL_dscale,
                            float4* __restrict__ dL_drot, float* __restrict__ dL_dcov3D_out,
-                           const float4* __restrict__ packed, float* __restrict__ dL_dopacity_out) {
+                           const float4* __restrict__ packed, float* __restrict__ dL_dopacity_out,
+                           float* __restrict__ zero_cov3D) {
   __shared__ float s_sh[kThreads * kShStride];
   gsb_pdl_wait();
   gsb_pdl_launch_dependents();
@@ -356,6 +357,10 @@ preprocess_backward_kernel(const FrameK f, const int n, const float* __restrict_
       dc[0] = in_dcol[0], dc[1] = in_dcol[1], dc[2] = in_dcol[2];
       dL_dopacity_out[i] = in_dopac;
     }
+    if (zero_cov3D) {   // backward.py:1119,1195: the operator returns dL_dcov3D as a zero buffer (8-byte aligned here)
+      float2* z = reinterpret_cast<float2*>(zero_cov3D + (size_t)i * 6);
+      z[0] = z[1] = z[2] = make_float2(0.0f, 0.0f);
+    }
     if (dL_dcov3D_out) {
       float2* o = reinterpret_cast<float2*>(dL_dcov3D_out + (size_t)i * 6);
       o[0] = make_float2(o_dcov[0], o_dcov[1]);
@@ -387,7 +392,7 @@ GSB_API int gsb_preprocess_backward(gsb_ctx* ctx, gsb_stream s, const gsb_frame*
                                     float* dL_dcov3D_internal) {
   return gsb_preprocess_backward_impl(ctx, (cudaStream_t)s, f, n, means, radii, shs, scales, rotations, cov3Ds,
                                       clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale,
-                                      dL_drot, dL_dcov3D_internal, 0, nullptr, nullptr);
+                                      dL_drot, dL_dcov3D_internal, 0, nullptr, nullptr, nullptr);
 }
 
 GSB_API int gsb_preprocess_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const gsb_frame* f, int32_t n,
@@ -399,7 +404,7 @@ GSB_API int gsb_preprocess_backward_compact_sh(gsb_ctx* ctx, gsb_stream s, const
                                                float* dL_dcov3D_internal) {
   return gsb_preprocess_backward_impl(ctx, (cudaStream_t)s, f, n, means, radii, shs, scales, rotations, cov3Ds,
                                       clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs_compact,
-                                      dL_dscale, dL_drot, dL_dcov3D_internal, 1, nullptr, nullptr);
+                                      dL_dscale, dL_drot, dL_dcov3D_internal, 1, nullptr, nullptr, nullptr);
 }
 
 int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
@@ -407,8 +412,13 @@ int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* 
                                  const float* cov3Ds, const float* clamped_state, const float* dL_dmean2D,
                                  const float* dL_dconic, const float* dL_dcolor, float* dL_dmean3D, float* dL_dshs,
                                  float* dL_dscale, float* dL_drot, float* dL_dcov3D_internal, int sh_compact,
-                                 const float* packed, float* dL_dopacity_out) {
+                                 const float* packed, float* dL_dopacity_out, float* zero_cov3D) {
   if (!ctx) return GSB_ERR_INVALID;
+  if (zero_cov3D && (reinterpret_cast<uintptr_t>(zero_cov3D) & 7u) != 0) {
+    // an unaligned dL_dcov3D result buffer: zeroed by a stream operation instead of by the kernel
+    GSB_CUDA(ctx, cudaMemsetAsync(zero_cov3D, 0, sizeof(float) * 6 * (size_t)n, s));
+    zero_cov3D = nullptr;
+  }
   GSB_REQUIRE(ctx, f && n >= 0, "gsb_preprocess_backward: bad frame or n");
   if (n == 0) return GSB_OK;
   GSB_REQUIRE(ctx, gsb_aligned16(shs) && gsb_aligned16(dL_dshs) && gsb_aligned16(rotations) && gsb_aligned16(dL_drot),
@@ -424,7 +434,7 @@ int gsb_preprocess_backward_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* 
 #define GSB_PPB_LAUNCH(C, K)                                                                                              \
   GSB_LAUNCH(ctx, (preprocess_backward_kernel<C, K>), (int)gsb_div_up(n, kThreads), kThreads, 0, s, k, n, means, radii, shs, \
              scales, rotations, cov3Ds, clamped_state, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dshs, dL_dscale, \
-             reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal, pk, dL_dopacity_out)
+             reinterpret_cast<float4*>(dL_drot), dL_dcov3D_internal, pk, dL_dopacity_out, zero_cov3D)
   if (sh_compact && packed) GSB_PPB_LAUNCH(true, true);
   else if (sh_compact) GSB_PPB_LAUNCH(true, false);
   else if (packed) GSB_PPB_LAUNCH(false, true);

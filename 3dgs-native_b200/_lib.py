@@ -57,6 +57,9 @@ _SIGS = {
                                       C.c_uint64, vp, vp] + [f32] * 8 + [i32, i32]),
     "gsb_adam_step_peers_compact": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                               C.c_uint64, vp, vp] + [f32] * 8 + [i32, vp, i64, i32, i32]),
+    "gsb_adam_step_peers_phase": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                            C.c_uint64, C.c_uint64, vp, vp] + [f32] * 8 + [i32, vp, i64, i32, i32, i32]),
+    "gsb_set_color_dependency": (C.c_int, [vp, vp]),
     "gsb_fill_f32": (C.c_int, [vp, vp, vp, i64, f32]),
     "gsb_selftest_block_mask": (C.c_int, [vp, vp, i32, vp, vp, vp]),
     "gsb_selftest_work_counters": (C.c_int, [vp, vp, C.POINTER(Frame)] + [vp] * 6),

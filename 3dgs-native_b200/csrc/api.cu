@@ -154,6 +154,13 @@ GSB_API int gsb_reserve(gsb_ctx* ctx, gsb_stream s, int64_t num_rendered) {
   return gsb_reserve_binning(ctx, (cudaStream_t)s, num_rendered);
 }
 
+// See gsb200.h.  cuda_event: a cudaEvent_t (torch.cuda.Event.cuda_event), or NULL to clear.
+GSB_API int gsb_set_color_dependency(gsb_ctx* ctx, void* cuda_event) {
+  if (!ctx) return GSB_ERR_INVALID;
+  ctx->color_event = cuda_event;
+  return GSB_OK;
+}
+
 // A/B knobs (not part of the reference surface; results never depend on them)
 GSB_API int gsb_set_option(gsb_ctx* ctx, const char* name, int value) {
   if (!name || !ctx) return GSB_ERR_INVALID;
@@ -275,6 +282,25 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   // (the wait used to leave the GPU idle for 9-10 us per frame: scan -> read-back -> wake-up -> launch); when the
   // frame does not fit (first frame, the scene grew, a tile list beyond the class) the speculative kernels have done
   // nothing and the frame continues below as before.
+  // One-shot colour dependency (gsb_set_color_dependency): the SH coefficients are still being written on another
+  // stream -- the second phase of the multi-GPU exchange, which runs beside this frame's geometry preprocess and
+  // binning.  preprocess then leaves rgb / clamped_state to sh_color_kernel, which is queued behind a wait for the event,
+  // right in front of the blend.  An error return before that point hands the dependency back to the context.
+  struct ColorDep {
+    gsb_ctx* ctx;
+    void* ev;
+    ~ColorDep() {
+      if (ev) ctx->color_event = ev;
+    }
+  } color_dep{ctx, ctx->color_event};
+  ctx->color_event = nullptr;
+  const bool defer_color = color_dep.ev != nullptr;
+  auto finish_color = [&]() -> int {
+    if (!color_dep.ev) return GSB_OK;
+    GSB_CUDA(ctx, cudaStreamWaitEvent(s, (cudaEvent_t)color_dep.ev, 0));
+    color_dep.ev = nullptr;
+    return gsb_sh_color_impl(ctx, s, f, n, means, shs, radii, rgb, clamped_state);
+  };
   bool spec = false;
   int spec_cap = 0, spec_max = 0;
   if (ctx->opt.speculate && ctx->opt.binning == 0 && ctx->opt.tile_sort == 3 && ctx->last_num_rendered > 0 && n > 0) {
@@ -286,7 +312,7 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
   }
   {
     if ((rc = gsb_tile_binning_prepare(ctx, s, n, num_tiles)) != GSB_OK) return rc;
-    PreBin bin{ctx->tile_count};
+    PreBin bin{ctx->tile_count, defer_color ? 1 : 0};
     rc = gsb_preprocess_impl(ctx, s, f, n, means, scales, rotations, opacities, shs, radii, points_xy, depths, cov3Ds,
                              rgb, conic_opacity, ctx->tiles_touched, clamped_state, &bin);
     if (rc != GSB_OK) return rc;
@@ -316,6 +342,7 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
       rc = gsb_tile_binning_sort(ctx, s, n, f->width, f->height, points_xy, depths, radii, ranges, ctx->last_num_rendered,
                                  spec_max, point_list, go);
       if (rc != GSB_OK) return rc;
+      if ((rc = finish_color()) != GSB_OK) return rc;
       rc = gsb_blend_forward_impl(ctx, s_, f, ranges, point_list, points_xy, rgb, conic_opacity, depths, image, inv_depth,
                                   final_T, n_contrib, block_masks, go);
       if (rc != GSB_OK) return rc;
@@ -368,6 +395,7 @@ GSB_API int gsb_forward(gsb_ctx* ctx, gsb_stream s_, const gsb_frame* f, int32_t
       if (rc != GSB_OK) return rc;
     }
   }
+  if ((rc = finish_color()) != GSB_OK) return rc;   // (no-op when the speculative queue above has already done it)
   if (D == 0) {
     // forward.py:830: nothing is launched; every image-shaped output keeps its wp.zeros() state
     // (ranges were already written as all (0,0) by the counting pass)

@@ -67,6 +67,7 @@ struct gsb_ctx {
   int64_t n_cap = 0;
   int64_t last_num_rendered = 0;   // D and the longest tile list of the previous gsb_forward: what the next frame's
   int last_max_count = 0;          // speculative launch assumes
+  void* color_event = nullptr;     // gsb_set_color_dependency: one-shot, consumed by the next gsb_forward
   cudaStream_t side_stream = nullptr;   // gsb_forward: the point_offsets scan beside the speculative kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_count = nullptr;  // recorded behind the read-back of D: the host waits on it, not on the stream
@@ -375,7 +376,10 @@ void gsb_make_framek(const gsb_frame* f, FrameK* k);
 // Counting pass of the tile binning fused into preprocess (gsb_forward only): the per-tile counters.
 struct PreBin {
   int32_t* tile_count;
+  int defer_color;   // 1: rgb / clamped_state are left to gsb_sh_color_impl (the SH rows are not read)
 };
+int gsb_sh_color_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means, const float* shs,
+                      const int32_t* radii, float* rgb, float* clamped_state);
 int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means,
                         const float* scales, const float* rotations, const float* opacities, const float* shs,
                         int32_t* radii, float* points_xy, float* depths, float* cov3Ds, float* rgb,

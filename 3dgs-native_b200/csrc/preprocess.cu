@@ -17,12 +17,63 @@ constexpr int kShStride = 49;
 
 constexpr int kCntStride = 32;  // ints between two tiles' counters (tilesort.cu: one 128-byte line each)
 
+// SH -> RGB of one Gaussian (forward.py:304-362): sh = its 16 x 3 coefficients (row stride 3), o_rgb the colour
+// (clamped at 0 when f.clamped), o_cl the clamp flags.  Shared by preprocess_kernel and sh_color_kernel: one
+// expression order, one translation unit (-fmad=false), the same bits.
+__device__ __forceinline__ void gs_sh_to_rgb(const FrameK& f, const float px, const float py, const float pz,
+                                             const float* sh, float o_rgb[3], float o_cl[3]) {
+    float dx = px - f.campos[0], dy = py - f.campos[1], dz = pz - f.campos[2];
+    float len = sqrtf(gs_dot3(dx, dy, dz, dx, dy, dz));
+    float x = 0.f, y = 0.f, z = 0.f;  // [Warp] normalize: v/len if len > 0 else 0
+    if (len > 0.0f) {
+      x = dx / len;
+      y = dy / len;
+      z = dz / len;
+    }
+    float result[3];
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#define SHK(k) sh[(k) * 3 + c]
+      float r = GS_SH_C0 * SHK(0);
+      if (f.degree > 0) {
+        r = r - GS_SH_C1 * y * SHK(1) + GS_SH_C1 * z * SHK(2) - GS_SH_C1 * x * SHK(3);
+        if (f.degree > 1) {
+          r = r + GS_C2_0 * xy * SHK(4);
+          r = r + GS_C2_1 * yz * SHK(5);
+          r = r + GS_C2_2 * (2.0f * zz - xx - yy) * SHK(6);
+          r = r + GS_C2_3 * xz * SHK(7);
+          r = r + GS_C2_4 * (xx - yy) * SHK(8);
+          if (f.degree > 2) {
+            r = r + GS_C3_0 * y * (3.0f * xx - yy) * SHK(9);
+            r = r + GS_C3_1 * xy * z * SHK(10);
+            r = r + GS_C3_2 * y * (4.0f * zz - xx - yy) * SHK(11);
+            r = r + GS_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHK(12);
+            r = r + GS_C3_4 * x * (4.0f * zz - xx - yy) * SHK(13);
+            r = r + GS_C3_5 * z * (xx - yy) * SHK(14);
+            r = r + GS_C3_6 * x * (xx - 3.0f * yy) * SHK(15);
+          }
+        }
+      }
+#undef SHK
+      r = r + 0.5f;
+      result[c] = r;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o_cl[c] = (result[c] < 0.0f) ? 1.0f : 0.0f;  // forward.py:351-362
+      o_rgb[c] = f.clamped ? f_max(result[c], 0.0f) : result[c];
+    }
+}
+
 // BIN = true (gsb_forward): the kernel also runs the counting pass of the tile binning -- one
 // returning atomic per (Gaussian, tile) on the tile's counter, the arrival rank stored for the
 // scatter pass -- instead of a second kernel that re-derives every rectangle.  The rank slots of
 // a CTA's Gaussians are drawn from a global cursor (one atomic per CTA), so the pass needs no prefix
 // sum of tiles_touched; that scan (an output of the operator) runs off the critical path.
-template <bool BIN>
+// COLOR = false (gsb_forward with a colour dependency, see gsb_set_color_dependency): the SH rows are neither loaded
+// nor evaluated and rgb / clamped_state are left to sh_color_kernel.
+template <bool BIN, bool COLOR>
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, const float* __restrict__ scales,
                   const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
@@ -47,7 +98,7 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
   const float opacity = __ldg(opac + il);
 
   // cooperative, coalesced SH load (12 float4 per Gaussian), all twelve in flight
-  {
+  if (COLOR) {
     const float4* src = reinterpret_cast<const float4*>(shs + (size_t)base * 48);
     const int chunks = rows * 12;
     float4 v[12];
@@ -171,49 +222,7 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
     if ((rmaxx - rminx) * (rmaxy - rminy) == 0) break;  // forward.py:301
 
     // ---- SH -> RGB, forward.py:304-346 ----
-    float dx = px - f.campos[0], dy = py - f.campos[1], dz = pz - f.campos[2];
-    float len = sqrtf(gs_dot3(dx, dy, dz, dx, dy, dz));
-    float x = 0.f, y = 0.f, z = 0.f;  // [Warp] normalize: v/len if len > 0 else 0
-    if (len > 0.0f) {
-      x = dx / len;
-      y = dy / len;
-      z = dz / len;
-    }
-    const float* sh = s_sh + tid * kShStride;
-    float result[3];
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-#define SHK(k) sh[(k) * 3 + c]
-      float r = GS_SH_C0 * SHK(0);
-      if (f.degree > 0) {
-        r = r - GS_SH_C1 * y * SHK(1) + GS_SH_C1 * z * SHK(2) - GS_SH_C1 * x * SHK(3);
-        if (f.degree > 1) {
-          r = r + GS_C2_0 * xy * SHK(4);
-          r = r + GS_C2_1 * yz * SHK(5);
-          r = r + GS_C2_2 * (2.0f * zz - xx - yy) * SHK(6);
-          r = r + GS_C2_3 * xz * SHK(7);
-          r = r + GS_C2_4 * (xx - yy) * SHK(8);
-          if (f.degree > 2) {
-            r = r + GS_C3_0 * y * (3.0f * xx - yy) * SHK(9);
-            r = r + GS_C3_1 * xy * z * SHK(10);
-            r = r + GS_C3_2 * y * (4.0f * zz - xx - yy) * SHK(11);
-            r = r + GS_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHK(12);
-            r = r + GS_C3_4 * x * (4.0f * zz - xx - yy) * SHK(13);
-            r = r + GS_C3_5 * z * (xx - yy) * SHK(14);
-            r = r + GS_C3_6 * x * (xx - 3.0f * yy) * SHK(15);
-          }
-        }
-      }
-#undef SHK
-      r = r + 0.5f;
-      result[c] = r;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      o_cl[c] = (result[c] < 0.0f) ? 1.0f : 0.0f;  // forward.py:351-362
-      o_rgb[c] = f.clamped ? f_max(result[c], 0.0f) : result[c];
-    }
+    if (COLOR) gs_sh_to_rgb(f, px, py, pz, s_sh + tid * kShStride, o_rgb, o_cl);
     o_depth = p_view[2];
     o_radius = f2i(my_radius);
     o_x = pix;
@@ -240,6 +249,57 @@ preprocess_kernel(const FrameK f, const int n, const float* __restrict__ means, 
   c3[0] = make_float2(o_cov[0], o_cov[1]);
   c3[1] = make_float2(o_cov[2], o_cov[3]);
   c3[2] = make_float2(o_cov[4], o_cov[5]);
+  if (COLOR) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      rgb[3 * i + c] = o_rgb[c];
+      clamped_state[3 * i + c] = o_cl[c];
+    }
+  }
+}
+
+// The colour half of preprocess_kernel<.., COLOR = false>: rgb and clamped_state of every Gaussian (zeros for the
+// culled ones, radii == 0, like the wp.zeros outputs of forward.py:703-710).  Same CTA shape and SH staging.
+__global__ void __launch_bounds__(kPreThreads)
+sh_color_kernel(const FrameK f, const int n, const float* __restrict__ means, const float* __restrict__ shs,
+                const int* __restrict__ radii, float* __restrict__ rgb, float* __restrict__ clamped_state) {
+  __shared__ float s_sh[kPreThreads * kShStride];
+  gsb_pdl_wait();
+  gsb_pdl_launch_dependents();
+  const int base = blockIdx.x * kPreThreads;
+  const int tid = threadIdx.x;
+  const int rows = min(kPreThreads, n - base);
+  const int i = base + tid;
+  const bool live = i < n;
+  const int il = live ? i : base;
+  const float px = means[3 * il + 0], py = means[3 * il + 1], pz = means[3 * il + 2];
+  const int radius = radii[il];
+  {
+    const float4* src = reinterpret_cast<const float4*>(shs + (size_t)base * 48);
+    const int chunks = rows * 12;
+    float4 v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = tid + k * kPreThreads;
+      v[k] = (c < chunks) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int c = tid + k * kPreThreads;
+      if (c < chunks) {
+        const int g = c / 12, qd = c - g * 12;
+        float* d = s_sh + g * kShStride + qd * 4;
+        d[0] = v[k].x;
+        d[1] = v[k].y;
+        d[2] = v[k].z;
+        d[3] = v[k].w;
+      }
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  float o_rgb[3] = {0.f, 0.f, 0.f}, o_cl[3] = {0.f, 0.f, 0.f};
+  if (radius > 0) gs_sh_to_rgb(f, px, py, pz, s_sh + tid * kShStride, o_rgb, o_cl);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     rgb[3 * i + c] = o_rgb[c];
@@ -286,15 +346,30 @@ int gsb_preprocess_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_
   FrameK k;
   gsb_make_framek(f, &k);
   int grid = (int)gsb_div_up(n, kPreThreads);
-  if (bin) {
-    GSB_LAUNCH_PDL(ctx, preprocess_kernel<true>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
-               radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
+  if (bin && bin->defer_color) {
+    GSB_LAUNCH_PDL(ctx, (preprocess_kernel<true, false>), grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities,
+               shs, radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
+               reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, *bin);
+  } else if (bin) {
+    GSB_LAUNCH_PDL(ctx, (preprocess_kernel<true, true>), grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities,
+               shs, radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
                reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, *bin);
   } else {
-    GSB_LAUNCH_PDL(ctx, preprocess_kernel<false>, grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities, shs,
-               radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
+    GSB_LAUNCH_PDL(ctx, (preprocess_kernel<false, true>), grid, kPreThreads, 0, s, k, n, means, scales, rotations, opacities,
+               shs, radii, reinterpret_cast<float2*>(points_xy), depths, cov3Ds, rgb,
                reinterpret_cast<float4*>(conic_opacity), tiles_touched, clamped_state, PreBin{});
   }
+  return GSB_OK;
+}
+
+// rgb / clamped_state of a frame whose preprocess ran with bin->defer_color (gsb_forward with a colour dependency)
+int gsb_sh_color_impl(gsb_ctx* ctx, cudaStream_t s, const gsb_frame* f, int32_t n, const float* means, const float* shs,
+                      const int32_t* radii, float* rgb, float* clamped_state) {
+  if (n == 0) return GSB_OK;
+  FrameK k;
+  gsb_make_framek(f, &k);
+  GSB_LAUNCH_PDL(ctx, sh_color_kernel, (int)gsb_div_up(n, kPreThreads), kPreThreads, 0, s, k, n, means, shs, radii, rgb,
+             clamped_state);
   return GSB_OK;
 }
 

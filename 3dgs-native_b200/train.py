@@ -175,7 +175,7 @@ class FrameBuffers:
 
 class Trainer:
     def __init__(self, cameras, targets=None, num_points=None, params=None, config=None, device=None,
-                 rank=0, world_size=1, process_group=None, exchange="auto", sh_compact=True):
+                 rank=0, world_size=1, process_group=None, exchange="auto", sh_compact=True, overlap_sh=True):
         """``exchange`` selects how the gradient sum and the Adam step are done when world_size > 1:
         "nccl" = all_reduce + replicated Adam; "peers" / "multimem" / "hybrid" = the fused kernel of
         gsb_adam_step_peers over symmetric memory (NVLink loads and stores / NVSwitch in-fabric reduction and
@@ -185,7 +185,12 @@ class Trainer:
         ``sh_compact`` (peers only): on steps where every rank renders exactly one view, the ranks
         publish the SH gradient as its two rank-1 factors (8 instead of 48 floats per Gaussian,
         gsb_backward_compact_sh) and the owner of a Gaussian expands them -- same bits, a third of
-        the gradient bytes over NVLink."""
+        the gradient bytes over NVLink.
+        ``overlap_sh`` (fused exchange modes, ``train_step`` only): the exchange runs in two phases -- positions,
+        scales, rotations and opacities (11 of the 59 floats per Gaussian) between two barriers on the main stream, the
+        SH coefficients (48 of 59) on a side stream BESIDE the next step's geometry preprocess and binning, which do not
+        read them; the next forward evaluates the colours behind that stream's event (gsb_set_color_dependency).
+        Same kernels, same bits; steps with a densify event exchange in one piece."""
         self.config = GaussianParams.get_config_dict()
         if config:
             self.config.update(config)
@@ -194,6 +199,9 @@ class Trainer:
         self.rank, self.world_size, self.pg = rank, world_size, process_group
         self.exchange = self._pick_exchange(exchange)
         self.sh_compact = bool(sh_compact) and self.exchange in ("peers", "hybrid")
+        self.overlap_sh = bool(overlap_sh) and self.exchange in FUSED_EXCHANGES
+        self._side_stream = None     # second phase of the exchange (overlap_sh)
+        self._sh_event = None        # recorded behind it: the SH coefficients of every rank are final
         self._compact_step = False
         self.cameras = cameras
         bg = self.config["background_color"]
@@ -301,6 +309,12 @@ class Trainer:
         P, p, L = self.params, _lib.ptr, _lib.lib()
         D = C.c_int64(0)
         fb.has_point_offsets = bool(point_offsets)
+        sh_event, self._sh_event = self._sh_event, None
+        if sh_event is not None:
+            # the previous step's SH exchange may still be running on the side stream: this frame's geometry preprocess
+            # and binning do not read the SH coefficients; the colours are evaluated behind the event (one-shot; an
+            # error return hands it back to the context, so the retry below keeps it)
+            self.ctx.check(L.gsb_set_color_dependency(self.ctx.h, C.c_void_p(sh_event.cuda_event)))
         for _ in range(2):
             rc = L.gsb_forward(self.ctx.h, _lib.stream_ptr(self.ctx.device_index), C.byref(frame), self.num_points,
                                p(P["positions"]), p(P["scales"]), p(P["rotations"]), p(P["opacities"]), p(P["shs"]),
@@ -380,7 +394,14 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def exchange_and_step(self, iteration, compact=None, publish_position_grad=False):
+    def join_exchange(self):
+        """Make the current stream wait for a second exchange phase that is still in flight (overlap_sh): call before
+        anything other than ``forward`` reads the parameters or the SH moments."""
+        ev, self._sh_event = self._sh_event, None
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def exchange_and_step(self, iteration, compact=None, publish_position_grad=False, overlap=False):
         """``compact``: the SH segment of every rank's gradient buffer holds the rank-1 factors
         written by gsb_backward_compact_sh (None = whatever train_step decided for this step).
         ``publish_position_grad`` (fused modes; nccl leaves the sum in ``self.grads`` anyway): after
@@ -390,7 +411,10 @@ class Trainer:
         Gradient sum over the ranks + Adam.  nccl: all_reduce then the replicated fused Adam.
         peers / multimem: ONE kernel between two cross-rank barriers -- each rank reduces its shard
         of the gradients straight out of its peers' buffers, updates that shard, and writes the new
-        parameters into every rank's buffer (gsb_adam_step_peers)."""
+        parameters into every rank's buffer (gsb_adam_step_peers).
+        ``overlap`` (fused modes; ``train_step`` passes ``self.overlap_sh``): two phases, see ``__init__``; the caller
+        must not read SH coefficients or SH moments before ``forward`` / ``join_exchange``."""
+        self.join_exchange()
         if compact is not None:
             if compact and not self.sh_compact:
                 raise ValueError("compact SH exchange needs exchange='peers' or 'hybrid' and sh_compact=True")
@@ -413,6 +437,39 @@ class Trainer:
         G.barrier(channel=0)        # every rank's backward has finished writing its gradients
         if ev:
             ev[1].record()
+        if overlap:
+            L, cfg = _lib.lib(), self.config
+            sh_local = self.sh_local if self._compact_step else None
+
+            def phase(k):
+                self.ctx.check(L.gsb_adam_step_peers_phase(
+                    self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp,
+                    0 if self._compact_step else g_mc, p_mc, _lib.ptr(self.adam_m.flat), _lib.ptr(self.adam_v.flat),
+                    lr["lr_pos"], lr["lr_scale"], lr["lr_rot"], lr["lr_opac"], lr["lr_sh"], cfg["adam_beta1"],
+                    cfg["adam_beta2"], cfg["adam_epsilon"], iteration, _lib.ptr(sh_local),
+                    sh_local.numel() if sh_local is not None else 0, cfg["sh_degree"], int(bool(publish_position_grad)), k))
+
+            main = torch.cuda.current_stream(self.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
+            # both phases start behind the opening barrier (they touch disjoint segments of the gradient, moment and
+            # parameter buffers); the SH phase is the longer one and gets the side stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                phase(2)
+                P.barrier(channel=2)    # every rank's SH coefficients have landed everywhere (and nobody reads the
+                done = torch.cuda.Event()   # SH gradients any more)
+                done.record(side)
+            phase(1)
+            if ev:
+                ev[2].record()
+            P.barrier(channel=1)    # every rank's positions / scales / rotations / opacities have landed everywhere
+            if ev:
+                ev[3].record()
+                self.exchange_parts.append(ev)
+            self._sh_event = done
+            return
         if self._compact_step:
             self.ctx.check(_lib.lib().gsb_adam_step_peers_compact(
                 self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, W, self.rank, gp, pp, p_mc,
@@ -450,14 +507,15 @@ class Trainer:
         loss_sum = fb.loss_sum           # densify may drop the frame buffers; the scalar tensor stays alive
         # a function of the iteration and the config only: every rank decides alike
         publish = bool(densify) and self.densify_due(iteration)
+        overlap = self.overlap_sh and not publish     # a densify event needs every parameter at once
         if self.exchange_events is not None:     # bench.py: device time of the exchange + Adam part
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.exchange_and_step(iteration, publish_position_grad=publish)
+            self.exchange_and_step(iteration, publish_position_grad=publish, overlap=overlap)
             e1.record()
             self.exchange_events.append((e0, e1))
         else:
-            self.exchange_and_step(iteration, publish_position_grad=publish)
+            self.exchange_and_step(iteration, publish_position_grad=publish, overlap=overlap)
         if densify:
             self.densification_and_pruning(iteration)
         return loss_sum
@@ -498,6 +556,7 @@ class Trainer:
         log = {"cloned": 0, "split": 0, "split_removed": 0, "pruned": 0, "opacity_reset": False}
         i32 = torch.int32
         if self.densify_due(iteration):
+            self.join_exchange()     # (train_step exchanges in one piece on these iterations; other callers may not)
             n = self.num_points
             avg_grads = self._scratch("avg_grads", n, torch.float32)     # every kernel below writes all of its output
             optimizer.compute_grad_norms(self.grads["positions"], avg_grads, n)
@@ -569,6 +628,7 @@ class Trainer:
         """The full Adam moments as (m, v) flat CUDA tensors.  In the fused exchange modes a rank only ever
         updates the moments of its own shard of Gaussians (shard_range): the shards are put together with one
         all-reduce of buffers that are zero outside the owner's shard.  Collective when world_size > 1."""
+        self.join_exchange()
         if self.exchange not in FUSED_EXCHANGES:
             return self.adam_m.flat, self.adam_v.flat
         import torch.distributed as dist
@@ -613,6 +673,7 @@ class Trainer:
         from .utils.point_cloud_utils import load_ply
         params = load_ply(os.path.join(str(ckpt_dir), "point_cloud.ply"))
         st = np.load(os.path.join(str(ckpt_dir), "state.npz"))
+        self.join_exchange()
         self._replace(FlatGaussians(int(st["num_points"]), self.device).load(params))     # copied into the state buffers
         self.adam_m.flat.copy_(torch.from_numpy(st["adam_m"]))
         self.adam_v.flat.copy_(torch.from_numpy(st["adam_v"]))

@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem", "hybrid"])
     ap.add_argument("--bwd-packed", type=int, default=1,
                     help="A/B: 1 = backward tile kernel accumulates into packed records with vector REDs, 0 = nine scalar REDs")
+    ap.add_argument("--overlap-sh", type=int, default=1,
+                    help="A/B (fused exchange modes): 1 = the SH part of the exchange runs on a side stream beside the next "
+                         "step's geometry preprocess and binning, 0 = one exchange between two barriers")
     ap.add_argument("--sh-compact", type=int, default=1,
                     help="A/B (peers exchange): 1 = SH gradients cross NVLink as their rank-1 factors, 0 = in full")
     ap.add_argument("--densify-every", type=int, default=0,
@@ -382,6 +385,7 @@ def params_checksum(torch, flat):
 
 def replicas_identical(torch, dist, T):
     """All ranks hold the same num_points and the same parameter bits."""
+    T.join_exchange()
     c = params_checksum(torch, T.params.flat)
     got = [torch.empty_like(c) for _ in range(T.world_size)]
     dist.all_gather(got, c)
@@ -469,7 +473,7 @@ def ours(args):
     if densify_on:
         cfg.update(densify_config(args.densify_every))
     T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=args.exchange,
-                      sh_compact=bool(args.sh_compact), config=cfg)
+                      sh_compact=bool(args.sh_compact), overlap_sh=bool(args.overlap_sh), config=cfg)
     T.ctx.set_option("blend_cull", args.cull)
     T.ctx.set_option("bwd_reduce", args.bwd_reduce)
     T.ctx.set_option("tile_sort", args.tile_sort)
@@ -510,6 +514,7 @@ def ours(args):
         for _ in range(K):
             T.train_step(it, batch(it), densify=densify_on)
             it += 1
+        T.join_exchange()     # overlap_sh: the last step's SH phase (side stream) belongs to the timed region
         e1.record()
         barrier()
         rep_ms.append(max_over_ranks(e0.elapsed_time(e1)))
@@ -535,6 +540,7 @@ def ours(args):
     for _ in range(10):
         T.train_step(it, batch(it), densify=False)
         it += 1
+    T.join_exchange()
     barrier()
     # (medians: the first of these steps can wait a long time for a rank that is still reading its NVML counters)
     exchange_ms = max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in T.exchange_events])))
@@ -727,7 +733,10 @@ def ours(args):
             "config": workload_config(args.config, (n, w, h), args.densify_every),
             "repeats": repeats,
             "details": {"exchange": T.exchange + ("+sh_compact (SH gradients cross NVLink as their rank-1 factors: "
-                                                   "76 instead of 236 B per Gaussian and peer)" if T.sh_compact else ""),
+                                                   "76 instead of 236 B per Gaussian and peer)" if T.sh_compact else "")
+                        + ("+overlap_sh (two phases: 11 of 59 floats between the barriers of the main stream, the SH "
+                           "coefficients on a side stream beside the next step's geometry preprocess and binning; "
+                           "exchange_plus_adam_ms / exchange_parts then describe the first phase)" if T.overlap_sh else ""),
                         "step": {"nccl": "NCCL all-reduce of 59*N gradient floats + replicated Adam",
                                  "peers": "fused NVLink peer-load gradient reduction/Adam/parameter broadcast kernel",
                                  "multimem": "fused NVSwitch multimem gradient reduction/Adam/parameter broadcast kernel",

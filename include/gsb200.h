@@ -264,6 +264,28 @@ int gsb_adam_step_peers_compact(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t w
                                 int32_t iteration, float* sh_local, int64_t sh_local_floats, int32_t degree,
                                 int32_t publish_position_grad);
 
+/* The fused exchange in TWO phases, so that the larger one can run beside the next frame (no reference counterpart:
+ * the reference has no multi-GPU path; same arithmetic and the same bits as the one-call forms above):
+ *   phase 1: positions, scales, rotations, opacities (11 of the 59 floats per Gaussian; the published position
+ *            gradient of densify steps belongs here);   phase 2: the SH coefficients (48 of 59), compact or full;
+ *   phase 0: everything (= gsb_adam_step_peers / gsb_adam_step_peers_compact).
+ * sh_local == NULL selects the full SH exchange (grad_multicast / param_multicast as in gsb_adam_step_peers), otherwise
+ * the compact one (grad_multicast must be 0).  Typical use (Trainer(overlap_sh=True)): barrier, phase 1, barrier on the
+ * main stream; phase 2 + barrier on a side stream; the next gsb_forward is given that stream's event with
+ * gsb_set_color_dependency and evaluates the colours only behind it. */
+int gsb_adam_step_peers_phase(gsb_ctx* ctx, gsb_stream s, int32_t n, int32_t world, int32_t rank,
+                              const uint64_t* grad_ptrs_host, const uint64_t* param_ptrs_host, uint64_t grad_multicast,
+                              uint64_t param_multicast, float* m_flat, float* v_flat, float lr_pos, float lr_scale,
+                              float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
+                              int32_t iteration, float* sh_local, int64_t sh_local_floats, int32_t degree,
+                              int32_t publish_position_grad, int32_t phase);
+
+/* One-shot: the NEXT gsb_forward on this context reads the SH coefficients only behind `cuda_event` (a cudaEvent_t
+ * recorded on any stream; NULL clears).  That call runs preprocess without the SH -> RGB evaluation, bins, then makes
+ * its stream wait for the event and evaluates rgb / clamped_state with a second kernel right in front of the blend:
+ * identical outputs.  Everything else the frame reads (means, scales, rotations, opacities) must be final as usual. */
+int gsb_set_color_dependency(gsb_ctx* ctx, void* cuda_event);
+
 /* Diagnostic (no reference counterpart): the reference's per-pixel loops (forward.py:454-501, backward.py:633-706)
  * walked by one thread per pixel with the arithmetic contract, counting work and decisions on a rendered frame.
  * counters7 (device, 7 x uint64, zeroed by the call):

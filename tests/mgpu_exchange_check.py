@@ -45,19 +45,24 @@ def compact_exchange_is_bit_identical(rank, world, cams, targets, params):
     dist.barrier()
     start = (T.params.flat.clone(), T.adam_m.flat.clone(), T.adam_v.flat.clone())
     out = {}
-    for compact, G in ((False, G_full), (True, G_comp)):
+    # (compact, gradients, two-phase exchange with the SH phase on a side stream)
+    for compact, G, overlap in ((False, G_full, False), (True, G_comp, False), (False, G_full, True), (True, G_comp, True)):
         T.params.flat.copy_(start[0]); T.adam_m.flat.copy_(start[1]); T.adam_v.flat.copy_(start[2])
         torch.cuda.synchronize()
         dist.barrier()                                  # nobody pushes into a buffer that is being restored
         T.grads = G
-        T.exchange_and_step(3, compact=compact)
+        T.exchange_and_step(3, compact=compact, overlap=overlap)
+        assert (T._sh_event is not None) == overlap
+        T.join_exchange()
         torch.cuda.synchronize()
         dist.barrier()
-        out[compact] = T.params.flat.clone()
-    assert not torch.equal(out[False], start[0])
-    assert torch.equal(out[False], out[True]), "compact SH exchange differs from the full one"
+        out[(compact, overlap)] = (T.params.flat.clone(), T.adam_m.flat.clone(), T.adam_v.flat.clone())
+    assert not torch.equal(out[(False, False)][0], start[0])
+    for key in ((True, False), (False, True), (True, True)):
+        for a, b, what in zip(out[(False, False)], out[key], ("parameters", "first moments", "second moments")):
+            assert torch.equal(a, b), f"exchange compact={key[0]} overlap={key[1]}: {what} differ from the one-piece full exchange"
     if rank == 0:
-        print("compact SH exchange: parameters bit-identical to the full exchange")
+        print("compact SH exchange and the two-phase exchange: parameters and moments bit-identical to the full one-piece exchange")
 
 
 HAS_MULTICAST = False

@@ -177,3 +177,32 @@ def test_speculative_frames_match_waiting_frames(L):
         assert np.array_equal(a_img, b_img) and np.array_equal(a_dep, b_dep)
         for k in a_buf:
             assert np.array_equal(a_buf[k], b_buf[k]), k
+
+
+def test_forward_with_a_colour_dependency_gives_the_same_outputs(L):
+    """gsb_set_color_dependency: the next gsb_forward runs preprocess without the SH -> RGB evaluation and computes
+    rgb / clamped_state with a second kernel behind the event (the multi-GPU trainer lets the SH part of its exchange
+    run beside the frame's geometry preprocess and binning).  Every output must be identical; the dependency is one-shot."""
+    import ctypes as C
+    import gsb200  # noqa: F401
+    from gsb200 import forward
+    ctx = L.context()
+    keys = ("colors", "clamped_state", "radii", "point_list", "ranges", "n_contrib", "final_Ts", "conic_opacity", "depths")
+    for (n, w, h, smin, smax) in ((4000, 160, 96, 0.01, 0.05), (9000, 64, 48, 0.1, 0.4), (300, 160, 96, 0.01, 0.03)):
+        kw = _scene(n, w, h, smin, smax, n)
+        for spec in (1, 0):
+            ctx.set_option("speculate", spec)
+            try:
+                forward.render_gaussians(**kw)                      # (gives the speculative path its previous frame)
+                img0, dep0, buf0 = forward.render_gaussians(**kw)
+                ev = torch.cuda.Event()
+                ev.record()
+                ctx.check(L.lib().gsb_set_color_dependency(ctx.h, C.c_void_p(ev.cuda_event)))
+                img1, dep1, buf1 = forward.render_gaussians(**kw)
+                img2, dep2, buf2 = forward.render_gaussians(**kw)   # dependency consumed: the plain path again
+            finally:
+                ctx.set_option("speculate", 1)
+            for img, dep, buf in ((img1, dep1, buf1), (img2, dep2, buf2)):
+                assert torch.equal(img0, img) and torch.equal(dep0, dep)
+                for k in keys:
+                    assert torch.equal(buf0[k], buf[k]), (k, spec)

@@ -41,7 +41,7 @@ int gsb_check_cuda(gsb_ctx* ctx, cudaError_t e, const char* what) {
 // grow-only device buffer; contents are NOT preserved
 int gsb_grow(gsb_ctx* ctx, void** ptr, int64_t* cap, int64_t need_elems, size_t elem_size, cudaStream_t s) {
   if (need_elems <= *cap) return GSB_OK;
-  int64_t new_cap = need_elems + need_elems / 4 + 1024;
+  int64_t new_cap = need_elems + need_elems / 2 + 1024;   // 50% to spare: every growth is a cudaFree (device-wide wait) + cudaMalloc
   if (*ptr) {
     GSB_CUDA(ctx, cudaStreamSynchronize(s));
     GSB_CUDA(ctx, cudaFree(*ptr));

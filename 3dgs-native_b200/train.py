@@ -323,14 +323,14 @@ class Trainer:
                                p(fb.image), p(fb.depth), p(fb.final_T), p(fb.n_contrib), C.byref(D),
                                p(fb.block_masks))
             if rc == _lib.GSB_ERR_CAPACITY:
-                fb.capacity = int(D.value) + int(D.value) // 8 + 1024
+                fb.capacity = int(D.value) + int(D.value) // 2 + 1024     # 50% to spare: the scene grows by densify events
                 fb.point_list = torch.empty(fb.capacity, dtype=torch.int32, device=self.device)
                 fb.block_masks = torch.empty(fb.capacity, dtype=torch.int32, device=self.device)
                 continue
             self.ctx.check(rc)
             break
         fb.num_rendered = int(D.value)
-        self.ctx.capacity_hint = max(self.ctx.capacity_hint, fb.num_rendered + fb.num_rendered // 8)
+        self.ctx.capacity_hint = max(self.ctx.capacity_hint, fb.num_rendered + fb.num_rendered // 4)
         return fb
 
     def loss_and_pixel_gradients(self, fb: FrameBuffers, target):

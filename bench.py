@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peers", "multimem", "hybrid"])
     ap.add_argument("--bwd-packed", type=int, default=1,
                     help="A/B: 1 = backward tile kernel accumulates into packed records with vector REDs, 0 = nine scalar REDs")
+    ap.add_argument("--opt", action="append", default=[], help="A/B: gsb_set_option name=value (repeatable)")
     ap.add_argument("--overlap-sh", type=int, default=1,
                     help="A/B (fused exchange modes): 1 = the SH part of the exchange runs on a side stream beside the next "
                          "step's geometry preprocess and binning, 0 = one exchange between two barriers")
@@ -478,6 +479,9 @@ def ours(args):
     T.ctx.set_option("bwd_reduce", args.bwd_reduce)
     T.ctx.set_option("tile_sort", args.tile_sort)
     T.ctx.set_option("bwd_packed", args.bwd_packed)
+    for kv in args.opt:                      # any other A/B option of gsb_set_option, e.g. --opt speculate=0 --opt pdl=0
+        name, value = kv.split("=")
+        T.ctx.set_option(name, int(value))
 
     def batch(it):   # one view per rank per step, cycling through the poses
         return [(it * world + r) % N_CAMERAS for r in range(world)]

@@ -200,6 +200,8 @@ class Trainer:
         self.exchange = self._pick_exchange(exchange)
         self.sh_compact = bool(sh_compact) and self.exchange in ("peers", "hybrid")
         self.overlap_sh = bool(overlap_sh) and self.exchange in FUSED_EXCHANGES
+        # 1: both phases start behind the opening barrier; 2: the SH phase starts behind the first phase's barrier
+        self.overlap_order = int(overlap_sh) if self.overlap_sh else 0
         self._side_stream = None     # second phase of the exchange (overlap_sh)
         self._sh_event = None        # recorded behind it: the SH coefficients of every rank are final
         self._compact_step = False
@@ -455,12 +457,17 @@ class Trainer:
             side = self._side_stream
             # both phases start behind the opening barrier (they touch disjoint segments of the gradient, moment and
             # parameter buffers); the SH phase is the longer one and gets the side stream
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                phase(2)
-                P.barrier(channel=2)    # every rank's SH coefficients have landed everywhere (and nobody reads the
-                done = torch.cuda.Event()   # SH gradients any more)
-                done.record(side)
+            def sh_phase():
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    phase(2)
+                    P.barrier(channel=2)    # every rank's SH coefficients have landed everywhere (and nobody reads
+                    done = torch.cuda.Event()   # the SH gradients any more)
+                    done.record(side)
+                return done
+
+            if self.overlap_order != 2:
+                done = sh_phase()
             phase(1)
             if ev:
                 ev[2].record()
@@ -468,6 +475,8 @@ class Trainer:
             if ev:
                 ev[3].record()
                 self.exchange_parts.append(ev)
+            if self.overlap_order == 2:
+                done = sh_phase()
             self._sh_event = done
             return
         if self._compact_step:

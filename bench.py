@@ -75,7 +75,8 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], help="A/B: gsb_set_option name=value (repeatable)")
     ap.add_argument("--overlap-sh", type=int, default=1,
                     help="A/B (fused exchange modes): 1 = the SH part of the exchange runs on a side stream beside the next "
-                         "step's geometry preprocess and binning, 0 = one exchange between two barriers")
+                         "step's geometry preprocess and binning (both phases start behind the opening barrier), 2 = the "
+                         "same with the SH phase started behind the first phase's barrier, 0 = one exchange between two barriers")
     ap.add_argument("--sh-compact", type=int, default=1,
                     help="A/B (peers exchange): 1 = SH gradients cross NVLink as their rank-1 factors, 0 = in full")
     ap.add_argument("--densify-every", type=int, default=0,
@@ -474,7 +475,7 @@ def ours(args):
     if densify_on:
         cfg.update(densify_config(args.densify_every))
     T = train.Trainer(cams, targets=targets, params=params, rank=rank, world_size=world, exchange=args.exchange,
-                      sh_compact=bool(args.sh_compact), overlap_sh=bool(args.overlap_sh), config=cfg)
+                      sh_compact=bool(args.sh_compact), overlap_sh=args.overlap_sh, config=cfg)
     T.ctx.set_option("blend_cull", args.cull)
     T.ctx.set_option("bwd_reduce", args.bwd_reduce)
     T.ctx.set_option("tile_sort", args.tile_sort)

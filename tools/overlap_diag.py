@@ -1,3 +1,10 @@
+#!/usr/bin/env python
+"""Timeline of one multi-GPU training step with and without the two-phase exchange (Trainer(overlap_sh=...)): forward,
+loss + backward, the main stream's share of the exchange, the NEXT forward (which waits for the SH phase in front of its
+colour kernel) and how long the SH phase runs past the main stream's exchange.  Run under torchrun with >= 2 ranks:
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/overlap_diag.py
+"""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 import gsb200
@@ -7,7 +14,6 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = i
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n, w, h = 300000, 800, 800
-params, _, _ = scene.synthetic_scene(n, w, h, 0.005, 0.03, seed=1, with_target=False) if False else (None,None,None)
 import bench
 params, cams, targets, _ = bench.make_scene("C2")
 lrs = {k: v * bench.LR_SCALE for k, v in bench.BASE_LRS.items()}; lrs["final_lr_factor"] = bench.FINAL_LR_FACTOR

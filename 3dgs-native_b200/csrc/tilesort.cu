@@ -100,19 +100,18 @@ tile_scan_kernel(int num_tiles, const int* __restrict__ tile_count, int2* __rest
   my_max = __reduce_max_sync(0xffffffffu, my_max);
   if (lane == 0) s_max[warp] = my_max;
   __syncthreads();
-  if (tid == 0) {
-    int m = 0;
-    for (int w = 0; w < 32; ++w) m = max(m, s_max[w]);
+  if (warp == 0) {
+    const int m = __reduce_max_sync(0xffffffffu, s_max[lane]);   // 32 warps: one value per lane
+    if (lane != 0) return;
     out_total_max[0] = s_carry;
     out_total_max[1] = m;
     // the go-ahead of the kernels gsb_forward queued behind this one WITHOUT waiting for D on the host: they run only
     // if the frame fits what the host assumed (buffer capacity, the sort kernel's capacity class)
     out_total_max[2] = (s_carry > 0 && s_carry <= spec_cap && m <= spec_max) ? 1 : 0;
     // D and the longest list go straight to the host's (mapped, pinned) scalars: no copy operation sits in the
-    // stream between this kernel and the scatter pass (it cost ~2 us and broke the chain of dependent launches)
-    host_total_max[0] = s_carry;
+    // stream between this kernel and the scatter pass (copy + broken chain of dependent launches cost the step 12 us)
+    host_total_max[0] = s_carry;   // (visible to the host when the event behind this kernel has completed)
     host_total_max[1] = m;
-    __threadfence_system();
   }
 }
 

@@ -55,15 +55,15 @@ struct gsb_ctx {
   // tile-binning scratch: [num_tiles] counts + [num_tiles] write cursors
   int32_t* tile_count = nullptr;
   int64_t tile_cap = 0;
-  int64_t tile_clean = 0;  // leading ints of tile_count (and the rank cursor) known to be zero: tile_scan_kernel
-                           // re-zeroes what the counting pass touched, so a steady-state frame needs no memset
+  int64_t tile_clean = 0;  // leading ints of tile_count known to be zero: the scatter pass counts every counter
+                           // back down, so a steady-state frame needs no memset
   // per-Gaussian internal buffers for gsb_forward / gsb_backward
   int32_t* tiles_touched = nullptr;
   float* dcov3d = nullptr;
   float* bwd_acc = nullptr;      // [12 n] packed accumulation records of the backward tile kernel
   float* bwd_acc_stage = nullptr;  // the same for the stage-level gsb_blend_backward (grown on demand)
   int64_t bwd_acc_cap = 0;
-  int32_t* rank_base = nullptr;  // index of a Gaussian's first arrival rank (fused counting pass)
+  int32_t* rank_base = nullptr;  // [n] scratch: the inclusive scan of tiles_touched when the caller passed no point_offsets (global-sort path)
   int64_t n_cap = 0;
   int64_t last_num_rendered = 0;   // D and the longest tile list of the previous gsb_forward: what the next frame's
   int last_max_count = 0;          // speculative launch assumes

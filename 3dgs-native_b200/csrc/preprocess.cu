@@ -66,11 +66,10 @@ __device__ __forceinline__ void gs_sh_to_rgb(const FrameK& f, const float px, co
     }
 }
 
-// BIN = true (gsb_forward): the kernel also runs the counting pass of the tile binning -- one
-// returning atomic per (Gaussian, tile) on the tile's counter, the arrival rank stored for the
-// scatter pass -- instead of a second kernel that re-derives every rectangle.  The rank slots of
-// a CTA's Gaussians are drawn from a global cursor (one atomic per CTA), so the pass needs no prefix
-// sum of tiles_touched; that scan (an output of the operator) runs off the critical path.
+// BIN = true (gsb_forward): the kernel also runs the counting pass of the tile binning -- one RED per
+// (Gaussian, tile) on the tile's counter -- instead of a second kernel that re-derives every rectangle.
+// The pass needs no prefix sum of tiles_touched; that scan (an output of the operator) runs off the
+// critical path.
 // COLOR = false (gsb_forward with a colour dependency, see gsb_set_color_dependency): the SH rows are neither loaded
 // nor evaluated and rgb / clamped_state are left to sh_color_kernel.
 template <bool BIN, bool COLOR>

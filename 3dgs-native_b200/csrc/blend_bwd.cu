@@ -314,16 +314,18 @@ __device__ __forceinline__ void bwd_group_moments(float* tS, const float* tW, co
     }
   }
   __syncwarp();  // every lane has read its operands: the S tile may now take the results
-  *reinterpret_cast<float2*>(tS + fg * kDRow + 2 * ft) = make_float2(dm[0], dm[1]);
-  *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 2 * ft) = make_float2(dm[2], dm[3]);
+  // (12 floats at the head of each of its 16 rows: the padding columns 32..35 of the rows stay untouched -- they
+  // carry the metadata of an open group across batches, see blend_backward_mma_kernel)
+  *reinterpret_cast<float2*>(tS + fg * kSRow + 2 * ft) = make_float2(dm[0], dm[1]);
+  *reinterpret_cast<float2*>(tS + (fg + 8) * kSRow + 2 * ft) = make_float2(dm[2], dm[3]);
   if (ft < 2) {
-    *reinterpret_cast<float2*>(tS + fg * kDRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
-    *reinterpret_cast<float2*>(tS + (fg + 8) * kDRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
+    *reinterpret_cast<float2*>(tS + fg * kSRow + 8 + 2 * ft) = make_float2(dc[0], dc[1]);
+    *reinterpret_cast<float2*>(tS + (fg + 8) * kSRow + 8 + 2 * ft) = make_float2(dc[2], dc[3]);
   }
   __syncwarp();
-  m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow);
-  m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kDRow + 4);
-  col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kDRow + 8);
+  m03 = *reinterpret_cast<const float4*>(tS + (lane & 15) * kSRow);
+  m45 = *reinterpret_cast<const float2*>(tS + (lane & 15) * kSRow + 4);
+  col = *reinterpret_cast<const float4*>(tS + (lane & 15) * kSRow + 8);
 }
 
 // a hit none of the 32 pixels used sums to nine exact zeros: adding them would be a no-op
@@ -435,6 +437,13 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
   float* const tW = &sm.sw[warp][1][0][0];
   const unsigned char* const wlist = sm.widx[warp];
 
+  // The open tensor-core group survives the end of a batch: its S / W rows stay in the per-warp tiles, and the
+  // per-row metadata the flush needs (centre, conic, opacity, Gaussian id: 7 words) moves from the staging arrays --
+  // which the next batch overwrites -- into the padding columns of those rows.  (Flushing the partial group at every
+  // batch end cost 5.6% of the kernel's instructions: 2.5 batches per tile, half-empty groups.)
+  int gslot = 0;              // slot of the next hit in the current group
+  int carried = 0;            // rows [0, carried) of the group come from earlier batches (metadata in the padding)
+  float* pS = tS + lane;      // this lane's column of the S tile, row gslot (the W tile is 16 rows further)
   for (int hi = tile_max; hi > 0; hi -= NT) {
     const int n_in = min(NT, hi);
     __syncthreads();
@@ -471,8 +480,6 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
     if (my_max <= hi - n_in) continue;
     // entries that touch this warp's block and lie inside its replay range (position < my_max)
     const int wn = warp_compact_hits(sm.meta, cnt, my_mask, my_max, lane, sm.widx[warp]);
-    int gslot = 0;              // slot of the next hit in the current group
-    float* pS = tS + lane;      // this lane's column of the S tile, row gslot (the W tile is 16 rows further)
 
     // One replayed hit whose alpha is known and >= 1/255 (backward.py:655-683): returns s, w.
     auto replay_hit = [&](const float G, const float alpha, const int j, float& sv, float& wv) {
@@ -488,16 +495,28 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
 
     // Group of `count` hits complete (rows 0 .. count-1 of the tiles, list entries qbase ..): reduce
     // them over the 32 pixels on the tensor cores and add the results to the gradient arrays.
+    // qbase: list entry of the group's first row that was recorded in THIS batch (row `carried`)
     auto flush_group = [&](const int qbase, const int count) {
       float4 m03, col;
       float2 m45;
       bwd_group_moments(tS, tW, lane, fg, ft, m0, m1, m2, dp_row, dp_cols, m03, m45, col);
-      GSB_DCHECK(count >= 1 && count <= kGrp && qbase >= 0 && qbase + count <= wn);
+      // (+ 1: a group closed by the all-zero padding row has one row without a list entry; its sums are zero)
+      GSB_DCHECK(count >= 1 && count <= kGrp && carried <= count && qbase >= 0 && qbase + count - carried <= wn + 1);
       if (lane < count && bwd_group_nonzero(m03, m45, col)) {
-        const int je = wlist[qbase + lane];
-        const int gid = __float_as_int(sm.c[je].w);
+        float4 ga, gb;
+        int gid;
+        if (lane < carried) {
+          ga = *reinterpret_cast<const float4*>(tS + lane * kSRow + 32);
+          gb = *reinterpret_cast<const float4*>(tW + lane * kSRow + 32);   // conic.b, opacity, gid bits, -
+          gid = __float_as_int(gb.z);
+        } else {
+          const int je = wlist[qbase + lane - carried];
+          ga = sm.a[je];
+          gb = sm.b[je];
+          gid = __float_as_int(sm.c[je].w);
+        }
         float g[5];
-        bwd_group_gradients(sm.a[je], sm.b[je], (float)bx0, (float)by0, m03, m45, ddelx_dx, ddely_dy, g);
+        bwd_group_gradients(ga, gb, (float)bx0, (float)by0, m03, m45, ddelx_dx, ddely_dy, g);
         if (PACKED) {
           float* const rec = acc_packed + 12 * (size_t)gid;
           red_add_v4(rec, g[0], g[1], g[2], m03.x);
@@ -517,6 +536,7 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       }
       __syncwarp();  // results consumed before the next group overwrites the tile
       gslot = 0;
+      carried = 0;
       pS = tS + lane;
     };
 
@@ -548,7 +568,7 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       pS[kGrp * kSRow + kSRow] = wvB;
       gslot += 2;
       pS += 2 * kSRow;
-      if (gslot == kGrp) flush_group(q + 2 - kGrp, kGrp);
+      if (gslot == kGrp) flush_group(q + 2 - (kGrp - carried), kGrp);
     }
     if (q < wn) {  // odd tail
       const int j = wlist[q];
@@ -562,9 +582,33 @@ blend_backward_mma_kernel(const BlendParams P, const int2* __restrict__ ranges, 
       pS[0] = sv;
       pS[kGrp * kSRow] = wv;
       ++gslot;
+      pS += kSRow;
       ++q;
     }
-    if (gslot > 0) flush_group(q - gslot, gslot);
+    // q == wn here: the rows [carried, gslot) were recorded in this batch, from the list entries [wn - (gslot - carried), wn)
+    if (hi <= NT) {                       // the tile's last batch: what is open is flushed
+      if (gslot > 0) flush_group(wn - (gslot - carried), gslot);
+    } else if (gslot > carried) {         // rows recorded in this batch stay open
+      const int fresh = gslot - carried;  // their number (before the padding row)
+      if (gslot & 1) {                    // pairs must not straddle a group: an all-zero row (the flush skips it)
+        pS[0] = 0.0f;
+        pS[kGrp * kSRow] = 0.0f;
+        ++gslot;
+        pS += kSRow;
+      }
+      if (gslot == kGrp) {
+        flush_group(wn - fresh, kGrp);    // (the padding row filled the group)
+      } else {
+        if (lane >= carried && lane < carried + fresh) {
+          const int je = wlist[wn - fresh + lane - carried];
+          const float4 b4 = sm.b[je];
+          *reinterpret_cast<float4*>(tS + lane * kSRow + 32) = sm.a[je];
+          *reinterpret_cast<float4*>(tW + lane * kSRow + 32) = make_float4(b4.x, b4.y, sm.c[je].w, 0.0f);
+        }
+        __syncwarp();
+        carried = gslot;
+      }
+    }
   }
 }
 

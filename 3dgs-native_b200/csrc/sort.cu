@@ -589,7 +589,8 @@ int gsb_radix_sort_pingpong(gsb_ctx* ctx, cudaStream_t s, int64_t* k0, int32_t* 
     }
     if (!ctx->sort_coop_state) {
       GSB_CUDA(ctx, cudaMalloc((void**)&ctx->sort_coop_state, sizeof(uint32_t) * kCoopStateWords));
-      GSB_CUDA(ctx, cudaMemsetAsync(ctx->sort_coop_state, 0, sizeof(uint32_t) * kCoopStateWords, s));
+      // (once per context, blocking: the first sort on ANOTHER stream must not overtake an asynchronous memset)
+      GSB_CUDA(ctx, cudaMemset(ctx->sort_coop_state, 0, sizeof(uint32_t) * kCoopStateWords));
     }
     int chunk = (int)(gsb_div_up(gsb_div_up(n, (int64_t)sms), 32) * 32);
     if (chunk < 2048) chunk = 2048;

@@ -216,6 +216,7 @@ struct BwdSmem {
   unsigned char widx[8][256];     // per warp: the staged entries it has to replay
   float sw[8][2][kGrp][kSRow];    // per warp: S tile (s per hit x pixel), W tile; the S tile is reused for results
 };
+static_assert(offsetof(BwdSmem, sw) % 16 == 0, "the S / W tiles are read with 16-byte loads");
 
 // TF32 head of x (mantissa truncated to 10 bits: one LOP3; cvt.rna.tf32 costs four instructions on
 // sm_100a).  x - tf32_hi(x) is exact, so hi + lo carries >= 20 mantissa bits through the MMA.

@@ -204,7 +204,6 @@ blend_backward_kernel(const BlendParams P, const int2* __restrict__ ranges, cons
 // 2 STS per hit plus ~13 instructions per hit amortised over the group.
 constexpr int kGrp = 16;   // hits per MMA group (the M dimension)
 constexpr int kSRow = 36;  // padded row length (floats) of the S / W tiles: conflict-free 16-byte reads
-constexpr int kDRow = 12;  // row length of the result tile (6 moments, 2 pad, 3 colours, 1 pad)
 
 struct BwdSmem {
   float4 a[256];   // x, y, conic.a, conic.c   (two packed pairs: see gs_power_packed)
@@ -252,18 +251,9 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; x mu
   return r;
 }
 
-// D[16x8] += A[16x8] * B[8x8], TF32 inputs, fp32 accumulate.  Fragment layout (PTX ISA, m16n8k8):
-//   A: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  B: b0 (k=t, n=g)  b1 (k=t+4, n=g);
-//   D: d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)      with g = lane >> 2, t = lane & 3
-__device__ __forceinline__ void mma_tf32(float d[4], float a0, float a1, float a2, float a3, float b0, float b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
-        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
-}
-
-// D[16x8] += A[16x4] * B[4x8] (m16n8k4): A: a0 (g, t) a1 (g+8, t);  B: b0 (k=t, n=g);  D as above.
+// D[16x8] += A[16x4] * B[4x8] (mma.sync m16n8k4, TF32 inputs, fp32 accumulate).  Fragment layout (PTX ISA):
+//   A: a0 (g, t)  a1 (g+8, t);  B: b0 (k=t, n=g);  D: d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)
+//   with g = lane >> 2, t = lane & 3.  (The m16n8k8 form needs four A operands live together: experiment 19.)
 __device__ __forceinline__ void mma_tf32_k4(float d[4], float a0, float a1, float b0) {
   asm volatile(
       "mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"

@@ -52,6 +52,7 @@ _SIGS = {
     "gsb_backward": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 26),
     "gsb_backward_compact_sh": (C.c_int, [vp, vp, C.POINTER(Frame), i32] + [vp] * 26),
     "gsb_adam_step": (C.c_int, [vp, vp, i32] + [vp] * 5 + [f32] * 8 + [i32] + [vp] * 15),
+    "gsb_adam_step_phase": (C.c_int, [vp, vp, i32] + [vp] * 5 + [f32] * 8 + [i32] + [vp] * 15 + [i32]),
     "gsb_flat_layout": (C.c_int, [i32, C.POINTER(i64), C.POINTER(i64)]),
     "gsb_adam_step_peers": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64,
                                       C.c_uint64, vp, vp] + [f32] * 8 + [i32, i32]),

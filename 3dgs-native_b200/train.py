@@ -199,7 +199,11 @@ class Trainer:
         self.rank, self.world_size, self.pg = rank, world_size, process_group
         self.exchange = self._pick_exchange(exchange)
         self.sh_compact = bool(sh_compact) and self.exchange in ("peers", "hybrid")
-        self.overlap_sh = bool(overlap_sh) and self.exchange in FUSED_EXCHANGES
+        # fused exchange modes: on by default.  One rank / nccl (``optimizer_step(overlap=True)``, the SH part of Adam
+        # beside the next frame's geometry preprocess and binning): only on request (``overlap_sh=3``) -- measured a
+        # wash on one B200, 676 against 681 us per step in tools/kbench.py but 685 against 680 us in bench.py: the two
+        # streams' kernels mostly take turns on the SMs instead of sharing them
+        self.overlap_sh = bool(overlap_sh) and (self.exchange in FUSED_EXCHANGES or int(overlap_sh) == 3)
         # 1: both phases start behind the opening barrier; 2: the SH phase starts behind the first phase's barrier
         self.overlap_order = int(overlap_sh) if self.overlap_sh else 0
         self._side_stream = None     # second phase of the exchange (overlap_sh)
@@ -308,7 +312,7 @@ class Trainer:
         scan is left out of the frame."""
         cam, frame = self.cameras[cam_index], self.frames[cam_index]
         fb = self._frame_buffers(cam)
-        P, p, L = self.params, _lib.ptr, _lib.lib()
+        P, p, L = self._params, _lib.ptr, _lib.lib()      # (not the property: see ``params``)
         D = C.c_int64(0)
         fb.has_point_offsets = bool(point_offsets)
         sh_event, self._sh_event = self._sh_event, None
@@ -365,9 +369,37 @@ class Trainer:
             return {k: s.get_lr(iteration, T) for k, s in self.lr_scheduler.items()}
         return {k: sc[k] for k in ("lr_pos", "lr_scale", "lr_rot", "lr_sh", "lr_opac")}
 
-    def optimizer_step(self, iteration):
-        """train.py:716-794."""
+    def optimizer_step(self, iteration, overlap=False):
+        """train.py:716-794.  ``overlap`` (``train_step`` passes ``self.overlap_sh``): the update of positions, scales,
+        rotations and opacities runs on the main stream, the update of the SH coefficients -- 81% of Adam's bytes -- on
+        a side stream BESIDE the next frame's geometry preprocess and binning, which do not read SH (they are bound
+        by atomics and latencies, Adam by HBM bandwidth); the next ``forward`` evaluates the colours behind that
+        stream's event.  Same kernel, same arithmetic, same bits."""
         lr, G, P, M, V = self.learning_rates(iteration), self.grads, self.params, self.adam_m, self.adam_v
+        if overlap:
+            L, cfg, p = _lib.lib(), self.config, _lib.ptr
+
+            def phase(k):
+                self.ctx.check(L.gsb_adam_step_phase(
+                    self.ctx.h, _lib.stream_ptr(self.ctx.device_index), self.num_points, p(G["positions"]), p(G["scales"]),
+                    p(G["rotations"]), p(G["opacities"]), p(G["shs"]), lr["lr_pos"], lr["lr_scale"], lr["lr_rot"],
+                    lr["lr_opac"], lr["lr_sh"], cfg["adam_beta1"], cfg["adam_beta2"], cfg["adam_epsilon"], iteration,
+                    p(P["positions"]), p(P["scales"]), p(P["rotations"]), p(P["opacities"]), p(P["shs"]),
+                    p(M["positions"]), p(M["scales"]), p(M["rotations"]), p(M["opacities"]), p(M["shs"]),
+                    p(V["positions"]), p(V["scales"]), p(V["rotations"]), p(V["opacities"]), p(V["shs"]), k))
+
+            main = torch.cuda.current_stream(self.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
+            side.wait_stream(main)          # the gradients are complete
+            with torch.cuda.stream(side):
+                phase(2)
+                done = torch.cuda.Event()
+                done.record(side)
+            phase(1)
+            self._sh_event = done
+            return
         optimizer.adam_update(G["positions"], G["scales"], G["rotations"], G["opacities"], G["shs"], self.num_points,
                               lr["lr_pos"], lr["lr_scale"], lr["lr_rot"], lr["lr_opac"], lr["lr_sh"],
                               self.config["adam_beta1"], self.config["adam_beta2"], self.config["adam_epsilon"], iteration,
@@ -396,6 +428,36 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
 
+    # The parameters and the Adam moments as everybody outside the step's hot path sees them: an access first joins a
+    # second phase (SH coefficients / their moments) that may still be running on the side stream (overlap_sh).
+    # ``forward`` alone uses ``_params``: its kernels read the SH coefficients only behind that stream's event.
+    @property
+    def params(self):
+        self.join_exchange()
+        return self._params
+
+    @params.setter
+    def params(self, value):
+        self._params = value
+
+    @property
+    def adam_m(self):
+        self.join_exchange()
+        return self._adam_m
+
+    @adam_m.setter
+    def adam_m(self, value):
+        self._adam_m = value
+
+    @property
+    def adam_v(self):
+        self.join_exchange()
+        return self._adam_v
+
+    @adam_v.setter
+    def adam_v(self, value):
+        self._adam_v = value
+
     def join_exchange(self):
         """Make the current stream wait for a second exchange phase that is still in flight (overlap_sh): call before
         anything other than ``forward`` reads the parameters or the SH moments."""
@@ -423,7 +485,7 @@ class Trainer:
             self._compact_step = bool(compact)
         if self.exchange in ("none", "nccl"):
             self.all_reduce_gradients()
-            self.optimizer_step(iteration)
+            self.optimizer_step(iteration, overlap=overlap)
             return
         G, P = self.grads.symm, self.params.symm
         lr = self.learning_rates(iteration)

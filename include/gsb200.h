@@ -227,6 +227,17 @@ int gsb_adam_step(gsb_ctx* ctx, gsb_stream s, int32_t n, const float* g_pos, con
                   float* m_scale, float* m_rot, float* m_opac, float* m_sh, float* v_pos, float* v_scale,
                   float* v_rot, float* v_opac, float* v_sh);
 
+/* gsb_adam_step for a subset of the tensors (no reference counterpart; same arithmetic, same bits): phase 1 = positions,
+ * scales, rotations, opacities; phase 2 = the SH coefficients (81% of the update's bytes); phase 0 = all.  A trainer may
+ * run phase 2 on a side stream beside the next frame's geometry preprocess and binning, which do not read SH, and hand
+ * that stream's event to the next gsb_forward with gsb_set_color_dependency (Trainer(overlap_sh=...)). */
+int gsb_adam_step_phase(gsb_ctx* ctx, gsb_stream s, int32_t n, const float* g_pos, const float* g_scale,
+                  const float* g_rot, const float* g_opac, const float* g_sh, float lr_pos, float lr_scale,
+                  float lr_rot, float lr_opac, float lr_sh, float beta1, float beta2, float epsilon,
+                  int32_t iteration, float* pos, float* scales, float* rots, float* opac, float* shs, float* m_pos,
+                  float* m_scale, float* m_rot, float* m_opac, float* m_sh, float* v_pos, float* v_scale,
+                  float* v_rot, float* v_opac, float* v_sh, int32_t phase);
+
 /* Layout of the "flat" per-role buffer used by the data-parallel trainer: positions | scales |
  * rotations | opacities | SH back to back, every segment starting on a 16-byte boundary.
  * offsets5 receives the five offsets in floats, *total the length in floats. */

@@ -63,7 +63,8 @@ def child(cfg, iters, out_path, opts=()):
     rng = np.random.default_rng(4242)
     targets = [rng.uniform(0, 1, (h, w, 3)).astype(np.float32) for _ in cams]
     lrs = {"lr_pos": 1e-6, "lr_scale": 5e-7, "lr_rot": 5e-7, "lr_sh": 2e-7, "lr_opac": 5e-7, "final_lr_factor": 0.01}
-    T = train.Trainer(cams, targets=targets, params=params, config={"num_iterations": 7000, "lr_scheduler_config": lrs})
+    T = train.Trainer(cams, targets=targets, params=params, config={"num_iterations": 7000, "lr_scheduler_config": lrs},
+                      overlap_sh=int(os.environ.get("GSB_OVERLAP_SH", "1")))   # 3: single-GPU Adam overlap
     L, ctx, p = _lib.lib(), T.ctx, _lib.ptr
     for kv in opts:
         k_, v_ = kv.split("=")
@@ -109,6 +110,7 @@ def child(cfg, iters, out_path, opts=()):
         e0.record()
         for it in range(20):
             T.train_step(10 + 20 * r + it, [it % 4], densify=False)
+        T.join_exchange()      # (overlap_sh: the last step's SH phase on the side stream belongs to the timed region)
         e1.record(); e1.synchronize()
         reps.append(e0.elapsed_time(e1) / 20)
     res["step_us"] = round(float(np.median(reps)) * 1e3, 1)
